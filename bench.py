@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the Lanczos hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): 1920x1080 -> 3840x2160 RGB8, 2x, Lanczos-3.  One "step" is
+one pass of the hot path over a batch of `--frames` distinct synthetic frames per GPU (the batch is
+~1 GB per GPU, far larger than the 126 MB L2, so every step streams from HBM).  Weak scaling: each
+GPU gets its own batch; no data-path collective; NCCL is used only for the barrier and the
+max-over-ranks of the step time.
+
+Prints ONE JSON line (see the contract in the task statement):
+  value        whole-job output Mpix/s, inputs resident in HBM, device-timed (CUDA events)
+  roofline     HBM roofline of the dominant kernel from a live CUDA-event timing
+  e2e          same metric through the host-buffer C-ABI call (pinned host memory, H2D+D2H inside)
+  cpu_baseline the reference's own software path (oracle/_ref) on this box's host cores
+`--impl reference` times that CPU path alone (rank 0; other ranks exit).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+IN_W, IN_H, OUT_W, OUT_H, CH, A, SN, SD = 1920, 1080, 3840, 2160, 3, 3, 2, 1
+WORKLOAD = "1920x1080->3840x2160 RGB8 2x Lanczos-3 (BASELINE configs[1])"
+ALGO_BYTES_PER_FRAME = IN_W * IN_H * CH + OUT_W * OUT_H * CH      # 31,104,000
+OUT_PX_PER_FRAME = OUT_W * OUT_H
+# CPU sample of the same workload: a 1920x135 band -> 3840x270 (1/8 frame), reference compiled for it
+CPU_SAMPLE_CFG = (1920, 135, 3840, 270, 2, 1, 3, 3)
+
+
+def measured_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+def ncu_traffic_per_launch(frames):
+    """DRAM bytes per launch from the committed ncu capture, scaled per frame (None if absent)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            t = json.load(fh)
+        return float(t["dram_bytes_per_frame"]) * frames
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks and throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        # median of the upper half = clocks under load (idle samples before/after drag the plain median down)
+        med = sm[(len(sm) * 3) // 4] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference_cpu(steps, warmup, threads=None):
+    """The reference's own software path (full_TB.h:29-96 compiled into oracle/_ref) on host cores."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import oracle_py as O
+    kind = "reference"
+    cfg = CPU_SAMPLE_CFG
+    iw, ih, ow, oh, n, d, a, c = cfg
+    cores = threads or os.cpu_count() or 1
+    have_ref = os.path.exists(O.ref_path(cfg))
+    if not have_ref:
+        kind = "port"
+    imgs = [O.xorshift_bytes(c * ih * iw, O.SEED + t).reshape(c, ih, iw) for t in range(cores)]
+
+    def one(t):
+        if have_ref:
+            O.ref_expected_planar(imgs[t], cfg)
+        else:  # literal per-tap-sin restatement, single thread per call like the reference
+            O.expected_planar(imgs[t], ow, oh, a, n, d, fast=False)
+
+    def step():
+        ths = [threading.Thread(target=one, args=(t,)) for t in range(cores)]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+
+    if have_ref:
+        O.ref_lib(cfg)
+    for _ in range(max(0, warmup)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    px = steps * cores * ow * oh
+    sample = (f"{cores} threads x {steps} steps, each thread one 1920x135->3840x270 RGB8 band (1/8 of a frame) of "
+              f"uniform noise through {'oracle/_ref (reference full_TB.h:29-96 compiled as is)' if have_ref else 'the oracle literal port'}")
+    return {"value": px / dt / 1e6, "unit": "Mpix/s", "cores": cores, "kind": kind, "sample": sample,
+            "seconds": dt, "ms_per_step": dt / steps * 1e3}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=32, help="frames per GPU per step")
+    ap.add_argument("--content", default="noise", choices=["noise", "smooth"])
+    ap.add_argument("--e2e-frames", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--flags", type=int, default=0)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1 and args.gpus > 1:
+        # launched directly: re-exec under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        os.execv(sys.executable, cmd)
+    n_gpus = world
+    warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        # bounded: 1/8-frame samples, at most ~2 minutes regardless of --steps
+        steps = max(1, min(args.steps, 40))
+        res = run_reference_cpu(steps, min(args.warmup, 2))
+        line = {
+            "impl": "reference", "metric": "output Mpix/s", "value": res["value"], "unit": "Mpix/s",
+            "n_gpus": n_gpus, "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": res["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": res["sample"]},
+            "cpu_baseline": {"value": res["value"], "unit": "Mpix/s", "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]},
+            "e2e": {"value": res["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line), flush=True)
+        return
+
+    import numpy as np
+    import torch
+    import lanczos_hls_b200 as lz
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    lz.lib()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    F = args.frames
+    g = torch.Generator(device=dev)
+    g.manual_seed(0x9E3779B9 + rank)
+    if args.content == "noise":
+        d_in = torch.randint(0, 256, (F, IN_H, IN_W, CH), dtype=torch.uint8, device=dev, generator=g)
+    else:
+        yy = torch.arange(IN_H, device=dev, dtype=torch.float32).view(1, IN_H, 1, 1)
+        xx = torch.arange(IN_W, device=dev, dtype=torch.float32).view(1, 1, IN_W, 1)
+        cc = torch.arange(CH, device=dev, dtype=torch.float32).view(1, 1, 1, CH)
+        ff = torch.arange(F, device=dev, dtype=torch.float32).view(F, 1, 1, 1)
+        base = 128 + 90 * torch.sin(0.05 * xx + cc + 0.3 * ff) * torch.cos(0.037 * yy)
+        noise = torch.randint(-8, 8, (F, IN_H, IN_W, CH), device=dev, generator=g)
+        d_in = (base + noise).clamp_(0, 255).to(torch.uint8)
+        del base, noise
+    d_out = torch.empty((F, OUT_H, OUT_W, CH), dtype=torch.uint8, device=dev)
+
+    def step(flags=args.flags):
+        lz.upscale_batch_device(d_in, d_out, a=A, scale_n=SN, scale_d=SD, flags=flags)
+
+    step()
+    torch.cuda.synchronize()
+    launches_per_step = lz.stats()["kernel_launches"]
+    kernel_id = lz.stats()["kernel_id"]
+    for _ in range(warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    # dominant kernel alone (ping-pong flag: no top-rows kernel), CUDA events on the launching stream
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(args.steps):
+        step(args.flags | lz.FLAG_NO_ALIAS)
+    k1.record()
+    torch.cuda.synchronize()
+    kernel_ms = k0.elapsed_time(k1) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = t.item() / args.steps
+    value = n_gpus * F * OUT_PX_PER_FRAME / (ms_per_step * 1e-3) / 1e6
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host memory) ----
+    e2e = None
+    if not args.no_e2e:
+        Fe = args.e2e_frames
+        hin = lz.PinnedBuffer(Fe * IN_H * IN_W * CH)
+        hout = lz.PinnedBuffer(Fe * OUT_H * OUT_W * CH)
+        hin.array[:] = d_in[:Fe].reshape(-1).cpu().numpy() if Fe <= F else np.resize(d_in.reshape(-1).cpu().numpy(), hin.nbytes)
+        h_in = hin.array.reshape(Fe, IN_H, IN_W, CH)
+        h_out = hout.array.reshape(Fe, OUT_H, OUT_W, CH)
+        e_steps = max(3, min(args.steps, 8))
+        lz.upscale(h_in, OUT_W, OUT_H, a=A, scale_n=SN, scale_d=SD, flags=args.flags, device=local_rank, out=h_out)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            lz.upscale(h_in, OUT_W, OUT_H, a=A, scale_n=SN, scale_d=SD, flags=args.flags, device=local_rank, out=h_out)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": n_gpus * Fe * e_steps * OUT_PX_PER_FRAME / te.item() / 1e6, "unit": "Mpix/s",
+               "h2d_bytes_per_step": Fe * IN_H * IN_W * CH, "d2h_bytes_per_step": Fe * OUT_H * OUT_W * CH,
+               "frames_per_step": Fe, "steps": e_steps, "ms_per_step": te.item() / e_steps * 1e3,
+               "api": "lanczos_b200_upscale_host (pinned host buffers, 3 streams)"}
+        hin.free()
+        hout.free()
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_hbm_peak()
+    achieved = F * ALGO_BYTES_PER_FRAME / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic_per_launch(F), "peak_source": peak_src,
+                "kernel": "main fused H->V kernel, one launch per step", "kernel_ms": kernel_ms,
+                "algorithmic_bytes_per_launch": F * ALGO_BYTES_PER_FRAME}
+    cpu = None
+    if n_gpus == 1 and not args.no_cpu_baseline:
+        r = run_reference_cpu(2, 0)
+        cpu = {"value": r["value"], "unit": "Mpix/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+    line = {
+        "metric": "output Mpix/s", "value": value, "unit": "Mpix/s", "n_gpus": n_gpus, "steps": args.steps,
+        "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 (f64 exact re-evaluation near integers)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": F, "content": args.content,
+                   "l2": f"inputs larger than L2: {F * ALGO_BYTES_PER_FRAME / 1e6:.0f} MB streamed per GPU per step",
+                   "kernel_id": kernel_id, "flags": args.flags},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

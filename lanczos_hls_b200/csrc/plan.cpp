@@ -1,0 +1,160 @@
+// plan.cpp -- descriptor validation, rational ratio, weight tables (host).
+// See plan.h for the reference interfaces this replaces.
+//
+// Compiled with -ffp-contract=off: the double weights must be the very values the
+// reference computes at full_TB.h:60 (`lanczos_kernel(x - i)` with x = (double)xx/SCALE).
+#include "plan.h"
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+namespace lzb {
+
+// full_TB.h:39-44
+static double sinc_ref(double x) {
+    if (x == 0) return 1;
+    return std::sin(x) / x;
+}
+
+// full_TB.h:51-53 (LANCZOS_A is an int macro: M_PI*x/a divides by (double)a)
+double ref_kernel(double x, int a) { return sinc_ref(M_PI * x) * sinc_ref(M_PI * x / a); }
+
+int resolve_desc(const lanczos_desc *in, lanczos_desc *out) {
+    if (!in || !out) return LANCZOS_ERR_NULL;
+    lanczos_desc d = *in;
+    if (d.in_w < 1 || d.in_h < 1 || d.out_w < 1 || d.out_h < 1) return LANCZOS_ERR_DIMS;
+    // 2^20 per side keeps every byte offset inside a row and every coordinate product in int32
+    if (d.in_w > (1 << 20) || d.in_h > (1 << 20) || d.out_w > (1 << 20) || d.out_h > (1 << 20))
+        return LANCZOS_ERR_DIMS;
+    if (d.channels < 1 || d.channels > 4) return LANCZOS_ERR_CHANNELS;
+    if (d.a < 1 || d.a > kMaxTaps / 2) return LANCZOS_ERR_TAPS;
+    if (d.reserved != 0) return LANCZOS_ERR_DIMS;
+    if (d.scale_n == 0 && d.scale_d == 0) {
+        // lanczos.h:110 SCALE_GCD = gcd(OUT_WIDTH, IN_WIDTH)
+        const int g = std::gcd(d.out_w, d.in_w);
+        d.scale_n = d.out_w / g;
+        d.scale_d = d.in_w / g;
+    } else {
+        if (d.scale_n < 1 || d.scale_d < 1) return LANCZOS_ERR_RATIO;
+        const int g = std::gcd(d.scale_n, d.scale_d);
+        d.scale_n /= g;
+        d.scale_d /= g;
+    }
+    if (d.scale_n < d.scale_d) return LANCZOS_ERR_RATIO;  // upscale only (worker.cpp:140)
+    if (d.scale_n > (1 << 16)) return LANCZOS_ERR_RATIO;
+    // the reference keeps the horizontal result in the first in_h rows of the output plane
+    if (d.out_h < d.in_h) return LANCZOS_ERR_DIMS;
+    const int64_t in_row = (int64_t)d.in_w * d.channels, out_row = (int64_t)d.out_w * d.channels;
+    if (d.in_pitch == 0) d.in_pitch = in_row;
+    if (d.out_pitch == 0) d.out_pitch = out_row;
+    if (d.in_pitch < in_row || d.out_pitch < out_row) return LANCZOS_ERR_DIMS;
+    *out = d;
+    return LANCZOS_OK;
+}
+
+static int build_axis(AxisTables &t, int out_len, int in_len, int a, int n, int dd,
+                      const std::vector<float> &phase_w) {
+    const int taps = 2 * a;
+    const double scale = (double)n / dd;  // lanczos.h:112
+    t.out_len = out_len;
+    t.in_len = in_len;
+    t.i0.resize(out_len);
+    t.wd.assign((size_t)out_len * taps, 0.0);
+    t.wf.assign((size_t)out_len * taps, 0.f);
+    t.aligned_exact = true;
+    t.fast_err = 0;
+    const double u = std::ldexp(1.0, -24);  // relative half-ulp of fp32
+    for (int xx = 0; xx < out_len; xx++) {
+        const double x = (double)xx / scale;  // full_TB.h:57,70
+        const double fx = std::floor(x);
+        const int64_t q = (int64_t)xx * dd / n;
+        if ((double)q != fx) return LANCZOS_ERR_RATIO_FLOAT;
+        const int phase = (int)(((int64_t)xx * dd) % n);
+        if (phase == 0 && x != fx) t.aligned_exact = false;
+        const int first = (int)q - a + 1;
+        t.i0[xx] = first;
+        double werr_coord = 0, werr_phase = 0, prefix_pos = 0, prefix_neg = 0, round_err = 0;
+        for (int k = 0; k < taps; k++) {
+            const int i = first + k;
+            const double w = ref_kernel(x - i, a);  // full_TB.h:60
+            const float wf = (float)w;
+            t.wd[(size_t)xx * taps + k] = w;
+            t.wf[(size_t)xx * taps + k] = wf;
+            werr_coord += 255.0 * std::fabs((double)wf - w);
+            werr_phase += 255.0 * std::fabs((double)phase_w[(size_t)phase * taps + k] - w);
+            if (wf > 0) prefix_pos += 255.0 * wf; else prefix_neg += -255.0 * wf;
+            round_err += u * (std::max(prefix_pos, prefix_neg) + 1.0);
+        }
+        t.fast_err = std::max(t.fast_err, std::max(werr_coord, werr_phase) + round_err);
+    }
+    return LANCZOS_OK;
+}
+
+int build_plan(const lanczos_desc *desc, Plan *out) {
+    Plan p;
+    int rc = resolve_desc(desc, &p.d);
+    if (rc != LANCZOS_OK) return rc;
+    const int a = p.d.a, n = p.d.scale_n, dd = p.d.scale_d;
+    p.taps = 2 * a;
+    // polyphase table: phase ph of the period-N pattern is first reached at output xx with
+    // (xx*D) mod N == ph; use that coordinate's weights (all coordinates of a phase agree to ~1e-13)
+    p.phase_w.assign((size_t)n * p.taps, 0.f);
+    p.phase_wd.assign((size_t)n * p.taps, 0.0);
+    {
+        const double scale = (double)n / dd;
+        std::vector<char> seen(n, 0);
+        for (int xx = 0; xx < n; xx++) {
+            const int ph = (int)(((int64_t)xx * dd) % n);
+            if (seen[ph]) continue;
+            seen[ph] = 1;
+            const double x = (double)xx / scale;
+            const int first = (int)((int64_t)xx * dd / n) - a + 1;
+            for (int k = 0; k < p.taps; k++) {
+                const double w = ref_kernel(x - (first + k), a);
+                p.phase_wd[(size_t)ph * p.taps + k] = w;
+                p.phase_w[(size_t)ph * p.taps + k] = (float)w;
+            }
+        }
+    }
+    rc = build_axis(p.x, p.d.out_w, p.d.in_w, a, n, dd, p.phase_w);
+    if (rc != LANCZOS_OK) return rc;
+    rc = build_axis(p.y, p.d.out_h, p.d.in_h, a, n, dd, p.phase_w);
+    if (rc != LANCZOS_OK) return rc;
+    // guard band: twice the rigorous fp32 error bound, never below 2^-13
+    const double e = std::max(p.x.fast_err, p.y.fast_err);
+    p.guard = (float)std::max(2.0 * e, std::ldexp(1.0, -13));
+
+    // in-place aliasing of the vertical pass (full_TB.h:67-77): going bottom-up, row xx reads
+    // rows first..last; any row i > xx has already been overwritten with final output.
+    p.alias_rows = 0;
+    p.alias_top_row = -1;
+    p.alias_in_rows = 0;
+    if (!(p.d.flags & LANCZOS_FLAG_NO_ALIAS)) {
+        auto last_row = [&](int xx) { return std::min(p.d.in_h - 1, p.y.i0[xx] + p.taps - 1); };
+        for (int xx = 0; xx < p.d.out_h; xx++)
+            if (last_row(xx) > xx) p.alias_rows = xx + 1;
+        for (int xx = 0; xx < p.alias_rows; xx++) p.alias_top_row = std::max(p.alias_top_row, last_row(xx));
+        for (int xx = 0; xx <= p.alias_top_row; xx++) p.alias_in_rows = std::max(p.alias_in_rows, last_row(xx) + 1);
+    }
+    *out = std::move(p);
+    return LANCZOS_OK;
+}
+
+void band_rows(const Plan &p, int out_row0, int out_rows, int *in_row0, int *in_rows) {
+    int lo = std::min(p.d.in_h - 1, std::max(0, p.y.i0[out_row0]));
+    int hi = std::min(p.d.in_h - 1, p.y.i0[out_row0 + out_rows - 1] + p.taps - 1);
+    if (out_row0 < p.alias_rows) {  // the in-place emulation starts from row alias_top_row
+        lo = 0;
+        hi = std::max(hi, p.alias_in_rows - 1);
+    }
+    if (hi < lo) hi = lo;  // band entirely below the last input row: nothing is read
+    *in_row0 = lo;
+    *in_rows = hi - lo + 1;
+}
+
+}  // namespace lzb

@@ -1,0 +1,54 @@
+// plan.h -- host-side plan: validated descriptor, rational ratio, weight tables.
+//
+// Replaces the reference's compile-time configuration and coefficient generator:
+//   params.h macros (template lanczos.h:9-31)        -> lanczos_desc, validated at run time
+//   gcd.h:1-24 + util_includes/simp (preprocessor gcd) -> std::gcd
+//   init_lanczos_kernel / LUT (kernel.cpp:40-58)      -> polyphase table, one row per phase
+//   lanczos_kernel(double) (full_TB.h:51-53)          -> per-coordinate double weights used by the
+//                                                        exact re-evaluation path
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "../../include/lanczos_b200.h"
+
+namespace lzb {
+
+constexpr int kMaxTaps = 8;  // 2*a, a <= 4
+
+// One axis (x: out_w/in_w, y: out_h/in_h) of the separable resampler.
+struct AxisTables {
+    int out_len = 0, in_len = 0;
+    std::vector<int32_t> i0;  // [out_len] first tap = floor(x)-a+1 (may be < 0)
+    std::vector<double> wd;   // [out_len][2a] L(x-(i0+k)) exactly as full_TB.h:60 evaluates it
+    std::vector<float> wf;    // [out_len][2a] the same rounded to float (fast path)
+    bool aligned_exact = true;  // every phase-0 coordinate has x exactly integral in double
+    double fast_err = 0;        // rigorous bound on |fp32 fast sum - reference double sum|
+};
+
+struct Plan {
+    lanczos_desc d{};  // resolved: ratio reduced, pitches filled
+    int taps = 0;      // 2a
+    AxisTables x, y;
+    std::vector<float> phase_w;  // [scale_n][2a] float polyphase table (phase p = (xx*D) mod N)
+    std::vector<double> phase_wd;  // [scale_n][2a] double, for reports
+    float guard = 0;             // |sum - nearest integer| below this -> exact re-evaluation
+    // in-place aliasing (full_TB.h:67-77): rows [0,alias_rows) read already-final rows
+    int alias_rows = 0;     // K0
+    int alias_top_row = -1; // M: largest row read by an aliased row (-1 if none)
+    int alias_in_rows = 0;  // input rows the alias emulation needs: 0..alias_in_rows-1
+};
+
+// Validate + resolve. Returns LANCZOS_OK or an error code.
+int resolve_desc(const lanczos_desc *in, lanczos_desc *out);
+
+// Build all host tables. `out` must outlive device uploads.
+int build_plan(const lanczos_desc *desc, Plan *out);
+
+// The reference kernel, full_TB.h:39-53.
+double ref_kernel(double x, int a);
+
+// Input row range needed for a band of output rows (global indices).
+void band_rows(const Plan &p, int out_row0, int out_rows, int *in_row0, int *in_rows);
+
+}  // namespace lzb

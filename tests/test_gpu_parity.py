@@ -1,0 +1,231 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle.
+Bar (BASELINE.json north_star): the software path is floating point, so <= 1 LSB is required;
+this implementation is expected to be BIT-EXACT (exact-match fraction 1.0), which is what is asserted.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from util import dark_hwc, diff_stats, golden_files, interleaved, noise_hwc, planar, smooth_hwc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def gpu_upscale(torch, lz, img, ow, oh, a, n, d, flags=0):
+    d_in = torch.from_numpy(img).cuda()
+    d_out = torch.empty((oh, ow, img.shape[2]), dtype=torch.uint8, device="cuda")
+    lz.upscale_device(d_in, d_out, a=a, scale_n=n, scale_d=d, flags=flags)
+    torch.cuda.synchronize()
+    return d_out.cpu().numpy()
+
+
+SMALL = [  # in_w, in_h, n, d, a, c
+    (96, 54, 2, 1, 3, 3), (96, 54, 2, 1, 2, 3), (96, 54, 3, 2, 3, 3), (100, 60, 17, 10, 3, 3),
+    (64, 48, 3, 2, 3, 4), (54, 30, 3, 1, 2, 3), (37, 23, 2, 1, 3, 4), (50, 40, 17, 10, 2, 3),
+    (33, 17, 4, 1, 3, 1), (131, 77, 2, 1, 3, 3), (129, 65, 3, 2, 3, 4), (70, 90, 5, 3, 3, 2),
+    (40, 40, 1, 1, 3, 3), (200, 37, 2, 1, 4, 3), (45, 200, 2, 1, 1, 4), (97, 101, 7, 4, 3, 3),
+]
+
+
+@pytest.mark.parametrize("cfg", SMALL, ids=lambda c: "x".join(map(str, c)))
+@pytest.mark.parametrize("kind", ["noise", "smooth", "dark"])
+def test_small_images_bit_exact(torch_cuda, lz, oracle, cfg, kind):
+    iw, ih, n, d, a, c = cfg
+    ow, oh = oracle.out_dims(iw, ih, n, d)
+    img = {"noise": noise_hwc, "smooth": smooth_hwc, "dark": dark_hwc}[kind](oracle, ih, iw, c, seed=iw)
+    want = oracle.upscale(img, ow, oh, a, n, d, variant=oracle.VERBATIM)
+    got = gpu_upscale(torch_cuda, lz, img, ow, oh, a, n, d)
+    st = diff_stats(got, want)
+    assert st["n_diff"] == 0, st
+    want_clean = oracle.upscale(img, ow, oh, a, n, d, variant=oracle.CLEAN)
+    got_clean = gpu_upscale(torch_cuda, lz, img, ow, oh, a, n, d, flags=lz.FLAG_NO_ALIAS)
+    assert np.array_equal(got_clean, want_clean)
+
+
+@pytest.mark.parametrize("path", golden_files(), ids=os.path.basename)
+def test_golden_fixtures_planar_api(torch_cuda, lz, path):
+    """Outputs of the reference's own lanczos_expected, through the same-shaped planar entry point."""
+    z = np.load(path)
+    iw, ih, ow, oh, n, d, a, c = (int(v) for v in z["cfg"])
+    got = lz.lanczos_expected(z["img_in"], ow, oh, a=a, scale_n=n, scale_d=d)
+    assert np.array_equal(got, z["img_out"])
+
+
+def test_structured_known_answers(torch_cuda, lz, oracle):
+    # all-0, all-255 (non-unit DC gain), impulse (reads back the weight table), step edges, checkerboard
+    h, w = 48, 64
+    imgs = {
+        "zero": np.zeros((h, w, 3), np.uint8),
+        "full": np.full((h, w, 3), 255, np.uint8),
+        "impulse": np.zeros((h, w, 3), np.uint8),
+        "vstep": np.zeros((h, w, 3), np.uint8),
+        "checker": np.zeros((h, w, 3), np.uint8),
+    }
+    imgs["impulse"][h // 2, w // 2] = 255
+    imgs["vstep"][:, w // 2:] = 255
+    yy, xx = np.mgrid[0:h, 0:w]
+    imgs["checker"][((yy + xx) & 1) == 1] = 255
+    for name, img in imgs.items():
+        for (n, d) in [(2, 1), (3, 2), (17, 10)]:
+            ow, oh = oracle.out_dims(w, h, n, d)
+            want = oracle.upscale(img, ow, oh, 3, n, d)
+            got = gpu_upscale(torch_cuda, lz, img, ow, oh, 3, n, d)
+            assert np.array_equal(got, want), (name, n, d)
+    assert not gpu_upscale(torch_cuda, lz, imgs["zero"], 128, 96, 3, 2, 1).any()
+
+
+def test_batch_equals_single_frames(torch_cuda, lz, oracle):
+    torch = torch_cuda
+    f, ih, iw, c, n, d = 5, 40, 56, 4, 3, 2
+    ow, oh = oracle.out_dims(iw, ih, n, d)
+    frames = np.stack([noise_hwc(oracle, ih, iw, c, seed=s) for s in range(f)])
+    d_in = torch.from_numpy(frames).cuda()
+    d_out = torch.zeros((f, oh, ow, c), dtype=torch.uint8, device="cuda")
+    lz.upscale_batch_device(d_in, d_out, a=3, scale_n=n, scale_d=d)
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy()
+    for i in range(f):
+        assert np.array_equal(got[i], oracle.upscale(frames[i], ow, oh, 3, n, d)), i
+
+
+def test_pitched_buffers(torch_cuda, lz, oracle):
+    torch = torch_cuda
+    ih, iw, c, n, d = 33, 50, 3, 2, 1
+    ow, oh = 100, 66
+    img = noise_hwc(oracle, ih, iw, c, seed=21)
+    in_pitch, out_pitch = iw * c + 13, ow * c + 29
+    buf_in = torch.zeros((ih, in_pitch), dtype=torch.uint8, device="cuda")
+    buf_in[:, : iw * c] = torch.from_numpy(img.reshape(ih, iw * c)).cuda()
+    buf_out = torch.full((oh, out_pitch), 0xAB, dtype=torch.uint8, device="cuda")
+    desc = lz.make_desc(iw, ih, ow, oh, c, 3, n, d, in_pitch, out_pitch)
+    rc = lz.lib().lanczos_b200_upscale(C.byref(desc), C.c_void_p(buf_in.data_ptr()), C.c_void_p(buf_out.data_ptr()), 0, None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    out = buf_out.cpu().numpy()
+    assert np.array_equal(out[:, : ow * c].reshape(oh, ow, c), oracle.upscale(img, ow, oh, 3, n, d))
+    assert (out[:, ow * c:] == 0xAB).all()   # padding untouched
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("cfg", [(120, 90, 17, 10, 3, 3), (64, 64, 2, 1, 3, 3), (90, 64, 3, 2, 3, 4)])
+def test_row_bands_concatenate_to_full(torch_cuda, lz, oracle, cfg, world):
+    """Each band sees only its own input rows (halo included) and uses global phases."""
+    torch = torch_cuda
+    from lanczos_hls_b200.sharding import band_range
+    iw, ih, n, d, a, c = cfg
+    ow, oh = oracle.out_dims(iw, ih, n, d)
+    img = noise_hwc(oracle, ih, iw, c, seed=world)
+    want = oracle.upscale(img, ow, oh, a, n, d)
+    desc = lz.make_desc(iw, ih, ow, oh, c, a, n, d)
+    out = np.zeros_like(want)
+    for rank in range(world):
+        r0, r1 = band_range(oh, rank, world)
+        in0, inn = lz.band_input_rows(desc, r0, r1 - r0)
+        d_in = torch.from_numpy(np.ascontiguousarray(img[in0:in0 + inn])).cuda()
+        d_out = torch.zeros((r1 - r0, ow, c), dtype=torch.uint8, device="cuda")
+        lz.upscale_band_device(desc, d_in, d_out, r0, r1 - r0, in0, inn)
+        torch.cuda.synchronize()
+        out[r0:r1] = d_out.cpu().numpy()
+    assert np.array_equal(out, want)
+
+
+def test_band_argument_errors(torch_cuda, lz):
+    torch = torch_cuda
+    desc = lz.make_desc(64, 64, 128, 128, 3, 3)
+    d_in = torch.zeros((10, 64, 3), dtype=torch.uint8, device="cuda")
+    d_out = torch.zeros((16, 128, 3), dtype=torch.uint8, device="cuda")
+    with pytest.raises(lz.LanczosError) as e:   # rows 32..47 need input rows 14..26, only 20..29 supplied
+        lz.upscale_band_device(desc, d_in, d_out, 32, 16, 20, 10)
+    assert e.value.code == -7
+    with pytest.raises(lz.LanczosError) as e:
+        lz.upscale_band_device(desc, d_in, d_out, 120, 16, 0, 10)
+    assert e.value.code == -7
+    assert lz.lib().lanczos_b200_upscale(C.byref(desc), None, None, 0, None) == -1
+
+
+def test_host_api_single_and_batch(torch_cuda, lz, oracle):
+    img = noise_hwc(oracle, 300, 200, 3, seed=4)           # single frame: pipelined as row bands
+    want = oracle.upscale(img, 400, 600, 3, 2, 1)
+    assert np.array_equal(lz.upscale(img, 400, 600), want)
+    frames = np.stack([noise_hwc(oracle, 40, 60, 4, seed=s) for s in range(9)])
+    got = lz.upscale(frames, 90, 60, n_streams=2)         # 3/2 derived from 90/60
+    for i in range(9):
+        assert np.array_equal(got[i], oracle.upscale(frames[i], 90, 60, 3, 3, 2)), i
+    many = lz.upscale_bands_multi_gpu(img, 400, 600, [0] * min(3, max(1, lz.device_count()) * 3))
+    assert np.array_equal(many, want)
+
+
+def test_packed_word_stream_shim(torch_cuda, lz, oracle):
+    """24-bit words, channel 0 in bits 7:0 (worker.cpp:35-43), raster order in and out."""
+    ih, iw = 30, 44
+    img = noise_hwc(oracle, ih, iw, 3, seed=8)
+    words = img[..., 0].astype(np.uint32) | (img[..., 1].astype(np.uint32) << 8) | (img[..., 2].astype(np.uint32) << 16)
+    out = lz.lanczos_stream(words, iw, ih, 88, 60).reshape(60, 88)
+    want = oracle.upscale(img, 88, 60, 3, 2, 1)
+    got = np.stack([(out >> (8 * i)) & 0xFF for i in range(3)], axis=-1).astype(np.uint8)
+    assert np.array_equal(got, want)
+    assert (out >> 24 == 0).all()
+
+
+def test_headline_config_full_size(torch_cuda, lz, oracle):
+    """BASELINE config 2: 1920x1080 -> 3840x2160 RGB8, 2x, Lanczos-3, uniform noise, full frame."""
+    img = noise_hwc(oracle, 1080, 1920, 3, seed=0)
+    want = oracle.upscale(img, 3840, 2160, 3, 2, 1)
+    got = gpu_upscale(torch_cuda, lz, img, 3840, 2160, 3, 2, 1)
+    st = diff_stats(got, want)
+    assert st["n_diff"] == 0, st
+
+
+def test_config3_rgba_three_halves_full_size(torch_cuda, lz, oracle):
+    """BASELINE config 3 (one frame of the batch): 2560x1440 -> 3840x2160 RGBA8, 3/2 via gcd."""
+    img = smooth_hwc(oracle, 1440, 2560, 4, seed=1)
+    want = oracle.upscale(img, 3840, 2160, 3, 3, 2)
+    got = gpu_upscale(torch_cuda, lz, img, 3840, 2160, 3, 0, 0)
+    assert np.array_equal(got, want)
+
+
+def test_config5_shape_reduced_and_properties(torch_cuda, lz, oracle):
+    """BASELINE config 5 geometry (x1.7 = 17/10, out = floor(in*17/10), unaligned output pitch) at
+    2048^2 against the oracle, and band == full at 4096^2 on the GPU alone (size-independent)."""
+    torch = torch_cuda
+    from lanczos_hls_b200.sharding import band_range
+    img = noise_hwc(oracle, 2048, 2048, 3, seed=2)
+    ow = oh = 2048 * 17 // 10
+    assert (ow * 3) % 16 != 0
+    want = oracle.upscale(img, ow, oh, 3, 17, 10)
+    assert np.array_equal(gpu_upscale(torch, lz, img, ow, oh, 3, 17, 10), want)
+    big = np.tile(img, (2, 2, 1))
+    bw = bh = 4096 * 17 // 10
+    full = gpu_upscale(torch, lz, big, bw, bh, 3, 17, 10)
+    desc = lz.make_desc(4096, 4096, bw, bh, 3, 3, 17, 10)
+    for rank in range(8):
+        r0, r1 = band_range(bh, rank, 8)
+        in0, inn = lz.band_input_rows(desc, r0, r1 - r0)
+        d_in = torch.from_numpy(np.ascontiguousarray(big[in0:in0 + inn])).cuda()
+        d_out = torch.zeros((r1 - r0, bw, 3), dtype=torch.uint8, device="cuda")
+        lz.upscale_band_device(desc, d_in, d_out, r0, r1 - r0, in0, inn)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_out.cpu().numpy(), full[r0:r1]), rank
+
+
+def test_determinism_and_strict_counter(torch_cuda, lz, oracle):
+    img = noise_hwc(oracle, 270, 480, 3, seed=6)
+    a = gpu_upscale(torch_cuda, lz, img, 960, 540, 3, 2, 1)
+    lz.enable_stats(True)
+    try:
+        b = gpu_upscale(torch_cuda, lz, img, 960, 540, 3, 2, 1)
+        st = lz.stats()
+    finally:
+        lz.enable_stats(False)
+    assert np.array_equal(a, b)
+    assert st["kernel_launches"] >= 1 and st["alias_rows"] == 5
+    assert st["strict_samples"] > 0      # noise always has sums near an integer
