@@ -195,7 +195,15 @@ int run_device(const DevicePlan &dp, unsigned flags, const uint8_t *d_in, uint8_
     if (n_frames <= 0 || out_rows <= 0) return LANCZOS_OK;
 
     int kid = 0;
-    cudaError_t e = (cudaError_t)launch_generic(p, s);
+    int frc = -1;
+    if (!(flags & LANCZOS_FLAG_GENERIC_KERNEL))
+        frc = launch_fast(p, h.phase_w.data(), h.align_k.data(), h.x.aligned_exact ? 1 : 0, h.y.aligned_exact ? 1 : 0, &kid, s);
+    if (frc > 0) return cuda_fail((cudaError_t)frc, "launch_fast");
+    cudaError_t e = cudaSuccess;
+    if (frc < 0) {
+        kid = 0;
+        e = (cudaError_t)launch_generic(p, s);
+    }
     if (e != cudaSuccess) return cuda_fail(e, "launch_generic");
     g_stats.kernel_launches++;
     g_stats.kernel_id = kid;

@@ -78,7 +78,7 @@ static int build_axis(AxisTables &t, int out_len, int in_len, int a, int n, int 
         if (phase == 0 && x != fx) t.aligned_exact = false;
         const int first = (int)q - a + 1;
         t.i0[xx] = first;
-        double werr_coord = 0, werr_phase = 0, prefix_pos = 0, prefix_neg = 0, round_err = 0;
+        double werr_coord = 0, werr_phase = 0, abs_sum = 0;
         for (int k = 0; k < taps; k++) {
             const int i = first + k;
             const double w = ref_kernel(x - i, a);  // full_TB.h:60
@@ -87,9 +87,10 @@ static int build_axis(AxisTables &t, int out_len, int in_len, int a, int n, int 
             t.wf[(size_t)xx * taps + k] = wf;
             werr_coord += 255.0 * std::fabs((double)wf - w);
             werr_phase += 255.0 * std::fabs((double)phase_w[(size_t)phase * taps + k] - w);
-            if (wf > 0) prefix_pos += 255.0 * wf; else prefix_neg += -255.0 * wf;
-            round_err += u * (std::max(prefix_pos, prefix_neg) + 1.0);
+            abs_sum += 255.0 * std::fabs(w);
         }
+        // any summation order: each of the `taps` FMAs rounds a partial sum bounded by abs_sum
+        const double round_err = taps * u * (abs_sum + 1.0);
         t.fast_err = std::max(t.fast_err, std::max(werr_coord, werr_phase) + round_err);
     }
     return LANCZOS_OK;
@@ -119,6 +120,19 @@ int build_plan(const lanczos_desc *desc, Plan *out) {
                 p.phase_wd[(size_t)ph * p.taps + k] = w;
                 p.phase_w[(size_t)ph * p.taps + k] = (float)w;
             }
+        }
+    }
+    // Phase 0 (coordinate exactly on an input sample): the reference's weights are 1 at the centre
+    // tap and ~1e-17 sin(k*pi) residues elsewhere (full_TB.h:43 has no |x|<a window).  Its double
+    // sum can only fall below v (and truncate to v-1) if the negative residues outweigh half the
+    // spacing of doubles below v, which is >= v*2^-54.  Sufficient for "output == v":
+    //     sum_k K_k * b_k <= v,   K_k = |w_k| * 2^54 / 0.99 for residues w_k < 0 (else 0).
+    p.align_k.assign(p.taps, 0.f);
+    for (int k = 0; k < p.taps; k++) {
+        const double w = p.phase_wd[k];
+        if (k != a - 1 && w < 0) {
+            const double K = -w * std::ldexp(1.0, 54) / 0.99;
+            if (K > 1e-7) p.align_k[k] = (float)(K * (1.0 + 1e-6));
         }
     }
     rc = build_axis(p.x, p.d.out_w, p.d.in_w, a, n, dd, p.phase_w);

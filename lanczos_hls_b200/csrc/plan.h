@@ -33,6 +33,7 @@ struct Plan {
     std::vector<float> phase_w;  // [scale_n][2a] float polyphase table (phase p = (xx*D) mod N)
     std::vector<double> phase_wd;  // [scale_n][2a] double, for reports
     float guard = 0;             // |sum - nearest integer| below this -> exact re-evaluation
+    std::vector<float> align_k;  // [2a] phase-0 "cannot flip" filter constants (see plan.cpp)
     // in-place aliasing (full_TB.h:67-77): rows [0,alias_rows) read already-final rows
     int alias_rows = 0;     // K0
     int alias_top_row = -1; // M: largest row read by an aliased row (-1 if none)
