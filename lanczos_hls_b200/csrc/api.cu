@@ -196,8 +196,11 @@ int run_device(const DevicePlan &dp, unsigned flags, const uint8_t *d_in, uint8_
 
     int kid = 0;
     int frc = -1;
-    if (!(flags & LANCZOS_FLAG_GENERIC_KERNEL))
-        frc = launch_fast(p, h.phase_w.data(), h.align_k.data(), h.x.aligned_exact ? 1 : 0, h.y.aligned_exact ? 1 : 0, &kid, s);
+    if (!(flags & LANCZOS_FLAG_GENERIC_KERNEL)) {
+        FastHostTables t{h.phase_w.data(), h.phase_wd.data(), h.align_k.data(), h.x.aligned_exact ? 1 : 0,
+                         h.y.aligned_exact ? 1 : 0, h.x.uniform_phase ? 1 : 0, h.y.uniform_phase ? 1 : 0};
+        frc = launch_fast(p, t, &kid, s);
+    }
     if (frc > 0) return cuda_fail((cudaError_t)frc, "launch_fast");
     cudaError_t e = cudaSuccess;
     if (frc < 0) {

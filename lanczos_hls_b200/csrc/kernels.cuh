@@ -31,8 +31,14 @@ struct KParams {
 int launch_generic(const KParams &p, cudaStream_t s);
 // Specialised TMA + register-window kernels (lanczos_fast.cu). Returns 0 when launched, a positive
 // cudaError_t on failure, -1 when no specialisation applies (the caller then uses the generic kernel).
-int launch_fast(const KParams &p, const float *phase_w_host, const float *align_k_host, int exact_x, int exact_y,
-                int *kernel_id, cudaStream_t s);
+struct FastHostTables {            // host-side views of the plan the specialised kernels need
+    const float *phase_w;          // [N][2a]
+    const double *phase_wd;        // [N][2a]
+    const float *align_k;          // [2a]
+    int exact_x, exact_y;          // AxisTables.aligned_exact
+    int uniform_x, uniform_y;      // AxisTables.uniform_phase
+};
+int launch_fast(const KParams &p, const FastHostTables &t, int *kernel_id, cudaStream_t s);
 // In-place top rows (full_TB.h:67-77 aliasing), exact double arithmetic.
 int launch_alias_rows(const KParams &p, cudaStream_t s);
 // Planar <-> interleaved helpers for lanczos_b200_expected / lanczos_b200_stream.

@@ -26,6 +26,7 @@
 // filter of plan.cpp and recomputed exactly when it fails.  Recomputations are deferred to
 // per-CTA lists so that they run 32 lanes wide.
 #include <algorithm>
+#include <type_traits>
 #include <cuda.h>
 
 #include "../../include/lanczos_b200.h"
@@ -37,7 +38,6 @@ namespace {
 
 constexpr int F_THREADS = 256;
 constexpr int F_SW_MAX = 1024;   // strip width in output bytes (one 32-bit word per V thread)
-constexpr int F_LIST = 1536;     // deferred-recompute list entries per pass
 
 // ---------------------------------------------------------------------------------------------
 // PTX helpers
@@ -102,7 +102,7 @@ __device__ __forceinline__ uint32_t quantise4(float a, float b, float c, float d
 // parameters
 // ---------------------------------------------------------------------------------------------
 struct FastParams {
-    const uint8_t *in;    // input row `in_row0` of frame 0 (exact recomputation reads it directly)
+    const uint8_t *in;    // input row `in_row0` of frame 0 (not dereferenced by the kernel; TMA reads it)
     uint8_t *out;         // output row `out_row0` of frame 0
     long long in_pitch, out_pitch, in_frame_stride, out_frame_stride;
     int in_w, in_h, out_w, out_h;
@@ -111,12 +111,14 @@ struct FastParams {
     int groups;           // H-pass thread groups per strip row
     int seg_periods;      // vertical ratio-periods per segment
     int vperiod0;         // first vertical period covered by the launch (floor(out_row0 / N))
-    const double *wdx, *wdy;
+    const double *wdx, *wdy;  // per-coordinate double weights (exact recomputation, non-uniform phases)
     float guard;
     int exact_x, exact_y;     // every phase-0 coordinate exactly integral (plan AxisTables.aligned_exact)
+    int uniform_x, uniform_y; // double weights identical for all coordinates of a phase -> wdtab usable
     int strict_v_identity;    // 0 with LANCZOS_FLAG_FAST_ALIGNED
     float align_k[8];         // phase-0 "cannot flip" constants
     float wtab[32 * 8];       // polyphase table [N][8] (padded to 8 taps), N <= 32
+    double wdtab[8 * 8];      // double polyphase table [N][8] for N <= 8 (valid when uniform_*)
     unsigned long long *strict_counter;
 };
 
@@ -135,53 +137,38 @@ struct Geo {
     static constexpr int NWORDS = (MIS + WIN_B + 3) / 4;
     static constexpr int MAX_GROUPS = F_SW_MAX / OUT_B;
     static constexpr int BOX_B = 16 * ((PAD_L + MAX_GROUPS * IN_B + HALO_R + 15) / 16);  // TMA box row bytes
-    static constexpr int RB = 12;                                 // input rows per chunk (multiple of TAPS)
-    static constexpr int RING = RB + TAPS + 2;                    // intermediate rows kept in smem
+    static constexpr int RB = 12;                                 // input rows per chunk
+    static constexpr int RING = 32;                               // intermediate rows kept in smem (power of 2)
     static constexpr int STAGE_B = 128 * ((RB * BOX_B + 127) / 128);  // TMA destinations must be 128-byte aligned
+    // the first row pushed by a segment is rs = D*pv0 - A + 1, so (row - A) mod D is static per chunk row
+    static constexpr int S0 = (((1 - 2 * A) % D) + D) % D;
+    static constexpr int UNR = (TAPS % D == 0) ? TAPS : TAPS * D; // rows per statically unrolled V block (multiple of TAPS and D)
+    static constexpr int YSPAN = (UNR + S0) * N / D + 2;          // bound on output rows touched per V block
     static_assert(IN_B % 4 == 0, "H item input must be word aligned");
     static_assert(OUT_B % 16 == 0, "H item output must be 16-byte aligned");
-    static_assert(RB % TAPS == 0, "chunk must be a multiple of the register-window rotation");
+    static_assert(RB % UNR == 0, "chunk must be a multiple of the unrolled V block");
+    static_assert(RING >= 2 * RB + TAPS, "ring too small for barrier-free V/H overlap");
     static_assert(BOX_B / 4 <= 256, "TMA box too wide");
     static_assert(N <= 32, "phase table too large for kernel params");
+    static_assert(YSPAN <= 64, "fix mask too small");
 };
 
 template <class G>
 struct __align__(128) FastSmem {
     uint8_t in[2][G::STAGE_B];            // TMA destinations (double buffered), row lr at lr * BOX_B
-    uint8_t ring[G::RING][F_SW_MAX];      // H-pass results (uint8), row r lives in slot (r - rs) % RING
-    float wv[32][8];                      // V-pass copy of the polyphase table
-    uint32_t hlist[F_LIST], vlist[F_LIST];
+    uint8_t ring[G::RING][F_SW_MAX];      // H-pass results (uint8), row r lives in slot (r - rs) & (RING-1)
     unsigned long long bar[2];
-    int hcount, vcount;
 };
 
-// exact H sample: the reference's loop full_TB.h:58-63 for output byte `obyte` of input row gy
-template <int C, int A, int N, int D>
-__device__ __noinline__ uint8_t exact_h(const FastParams &p, const uint8_t *in_frame, int gy, int obyte) {
-    if (gy < 0 || gy >= p.in_h) return 0;
-    const int xx = obyte / C, c = obyte - xx * C;
-    const int first = (int)(((long long)xx * D) / N) - A + 1;
-    const uint8_t *row = in_frame + (long long)(gy - p.in_row0) * p.in_pitch;
-    const double *w = p.wdx + (long long)xx * (2 * A);
-    double sum = 0.0;
-#pragma unroll
-    for (int k = 0; k < 2 * A; k++) {
-        const int px = first + k;
-        const uint8_t v = (px >= 0 && px < p.in_w) ? row[(long long)px * C + c] : (uint8_t)0;
-        sum = __dadd_rn(sum, __dmul_rn((double)v, w[k]));
-    }
-    return quantise_f64(sum);
-}
+__host__ __device__ constexpr int cdiv_c(int a, int b) { return (a + b - 1) / b; }
 
-// exact V sample (full_TB.h:71-75 arithmetic) from the uint8 intermediate rows in the shared ring
-template <int TAPS, int RING>
-__device__ __noinline__ uint8_t exact_v(const uint8_t (*ring)[F_SW_MAX], const double *wd, int first_slot_row, int b) {
+// Exact restatement of full_TB.h:58-63 for one sample whose 2a taps are `stride` bytes apart in
+// shared memory (taps outside the image were zero-filled by TMA: 0*w adds +-0, same bits).
+template <int TAPS>
+__device__ __noinline__ uint8_t exact_taps(const uint8_t *tap0, int stride, const double *w) {
     double sum = 0.0;
 #pragma unroll
-    for (int k = 0; k < TAPS; k++) {
-        const uint8_t v = ring[(first_slot_row + k) % RING][b];
-        sum = __dadd_rn(sum, __dmul_rn((double)v, wd[k]));
-    }
+    for (int k = 0; k < TAPS; k++) sum = __dadd_rn(sum, __dmul_rn((double)tap0[k * stride], w[k]));
     return quantise_f64(sum);
 }
 
@@ -190,12 +177,12 @@ __global__ void __launch_bounds__(F_THREADS, 2)
 lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ FastParams p) {
     using G = Geo<C, A, N, D, PH>;
     constexpr int TAPS = G::TAPS;
+    constexpr int RMASK = G::RING - 1;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     FastSmem<G> &sm = *reinterpret_cast<FastSmem<G> *>(smem_raw);
 
     const int tid = threadIdx.x;
     const int strip = blockIdx.x, seg = blockIdx.y, frame = blockIdx.z;
-    const uint8_t *in_frame = p.in + (long long)frame * p.in_frame_stride;
     uint8_t *out_frame = p.out + (long long)frame * p.out_frame_stride;
 
     // horizontal extent
@@ -219,10 +206,7 @@ lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
         mbar_init(bar0, 1);
         mbar_init(bar1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        sm.hcount = 0;
-        sm.vcount = 0;
     }
-    for (int i = tid; i < 32 * 8; i += F_THREADS) (&sm.wv[0][0])[i] = p.wtab[i];
     __syncthreads();
 
     constexpr uint32_t kStageBytes = G::RB * G::BOX_B;
@@ -244,18 +228,29 @@ lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
 #pragma unroll
         for (int e = 0; e < 4; e++) win[j][e] = 0.f;
     const bool v_active = 4 * tid < valid_bytes;
-    const float g2 = 2.f * p.guard;
+    const float guard = p.guard, g2 = 2.f * p.guard;
+    const long long opitch = p.out_pitch;
+    const uint8_t *vcol = &sm.ring[0][4 * tid];               // this thread's word column of the ring
+    uint8_t *ocol = out_frame + obyte0 + 4 * tid;
+    unsigned long long n_strict = 0;
+    // flag handling without loop-invariant branches (they would triple the unrolled code):
+    //   v_force   sign bit set  -> every phase-0 row is recomputed (inexact alignment, e.g. 17/10)
+    //   v_signmask 0            -> phase-0 rows are never recomputed (LANCZOS_FLAG_FAST_ALIGNED)
+    const uint32_t v_force = p.exact_y ? 0u : 0x80000000u;
+    const uint32_t v_signmask = (p.exact_y && !p.strict_v_identity) ? 0u : 0x80000000u;
+    const uint32_t h_force = p.exact_x ? 0u : 0x80000000u;
 
     for (int chunk = 0; chunk < nchunks; chunk++) {
         const int st = chunk & 1;
         mbar_wait(st ? bar1 : bar0, (chunk >> 1) & 1);
         const int r0 = rs + chunk * G::RB;                    // first row of this chunk
+        const int slot0 = (chunk * G::RB) & RMASK;            // ring slot of row r0
 
         // ------------------------------ H pass ------------------------------
         for (int item = tid; item < G::RB * groups; item += F_THREADS) {
             const int lr = item / groups, g = item - lr * groups;
-            const int gy = r0 + lr;
-            const uint32_t *src = reinterpret_cast<const uint32_t *>(&sm.in[st][lr * G::BOX_B + G::WIN0 + g * G::IN_B]);
+            const uint8_t *srow = &sm.in[st][lr * G::BOX_B];
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(srow + G::WIN0 + g * G::IN_B);
             float f[G::NWORDS * 4];
 #pragma unroll
             for (int wi = 0; wi < G::NWORDS; wi++)
@@ -266,7 +261,8 @@ lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
 #pragma unroll
             for (int ow = 0; ow < G::OUT_B / 4; ow++) {
                 float xa[4], xb[4];
-                bool flag = false;
+                uint32_t zor = 0;          // sign bit set <=> some phase-0 sample may flip (or must be recomputed)
+                bool has_p0 = false;
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
                     const int o = 4 * ow + e;              // output byte of the item
@@ -278,17 +274,14 @@ lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                         const float v = f[G::MIS + base + (A - 1) * C];
                         xa[e] = v;
                         xb[e] = v;
-                        if (p.exact_x) {
-                            float z = v;
+                        float z = v;                        // "cannot flip" filter of plan.cpp: z >= 0 -> output is v
 #pragma unroll
-                            for (int k = 0; k < TAPS; k++)
-                                if ((KM >> k) & 1) z = fmaf(f[G::MIS + base + k * C], -p.align_k[k], z);
-                            flag |= (z < 0.02f) && (v > 0.5f);
-                        } else {
-                            flag = true;                    // inexact alignment: always recompute
-                        }
+                        for (int k = 0; k < TAPS; k++)
+                            if ((KM >> k) & 1) z = fmaf(f[G::MIS + base + k * C], -p.align_k[k], z);
+                        zor |= __float_as_uint(z);
+                        has_p0 = true;
                     } else {
-                        float acc = -p.guard;
+                        float acc = -guard;
 #pragma unroll
                         for (int k = 0; k < TAPS; k++) acc = fmaf(f[G::MIS + base + k * C], p.wtab[ph * 8 + k], acc);
                         xa[e] = acc;
@@ -298,131 +291,119 @@ lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                 const uint32_t qa = quantise4(xa[0], xa[1], xa[2], xa[3]);
                 const uint32_t qb = quantise4(xb[0], xb[1], xb[2], xb[3]);
                 outw[ow] = qa;
-                if ((flag || qa != qb) && g * G::OUT_B + 4 * ow < valid_bytes) need_fix |= 1u << ow;
+                if (has_p0) zor |= h_force;                  // inexact alignment: phase-0 samples always recomputed
+                if (((qa ^ qb) | (zor & 0x80000000u)) != 0) need_fix |= 1u << ow;
             }
-            const int slot = (gy - rs) % G::RING;
-            uint4 *dst = reinterpret_cast<uint4 *>(&sm.ring[slot][g * G::OUT_B]);
+            uint8_t *drow = &sm.ring[(slot0 + lr) & RMASK][g * G::OUT_B];
+            uint4 *dst = reinterpret_cast<uint4 *>(drow);
 #pragma unroll
             for (int v4 = 0; v4 < G::OUT_B / 16; v4++)
                 dst[v4] = make_uint4(outw[4 * v4], outw[4 * v4 + 1], outw[4 * v4 + 2], outw[4 * v4 + 3]);
-            while (need_fix) {                               // rare: queue the word for exact recomputation
+            while (need_fix) {                               // rare: exact recomputation of one output word
                 const int ow = __ffs(need_fix) - 1;
                 need_fix &= need_fix - 1;
-                const int pos = atomicAdd(&sm.hcount, 1);
-                const uint32_t entry = ((uint32_t)lr << 16) | (uint32_t)(g * G::OUT_B + 4 * ow);
-                if (pos < F_LIST) {
-                    sm.hlist[pos] = entry;
-                } else {                                     // list full: recompute in place
-                    for (int e = 0; e < 4; e++)
-                        sm.ring[slot][g * G::OUT_B + 4 * ow + e] =
-                            exact_h<C, A, N, D>(p, in_frame, gy, obyte0 + g * G::OUT_B + 4 * ow + e);
+                if (g * G::OUT_B + 4 * ow >= valid_bytes) continue;
+#pragma unroll 1
+                for (int e = 0; e < 4; e++) {
+                    const int ob = obyte0 + g * G::OUT_B + 4 * ow + e;   // global output byte column
+                    const int xx = ob / C, c = ob - xx * C;
+                    const int first = (xx * D) / N - A + 1;                // first tap pixel (full_TB.h:59)
+                    const int ph = (xx * D) % N;
+                    const double *w = (p.uniform_x && N <= 8) ? &p.wdtab[ph * 8] : p.wdx + (long long)xx * TAPS;
+                    drow[4 * ow + e] = exact_taps<TAPS>(srow + G::PAD_L + first * C + c - ibyte0, C, w);
                 }
+                n_strict += 4;
             }
         }
         __syncthreads();
-        {   // deferred exact H samples, one lane per byte
-            const int n = min(sm.hcount, F_LIST);
-            if (n > 0) {
-                for (int i = tid; i < 4 * n; i += F_THREADS) {
-                    const uint32_t entry = sm.hlist[i >> 2];
-                    const int lr = entry >> 16, b = (entry & 0xffff) + (i & 3);
-                    const int gy = r0 + lr;
-                    sm.ring[(gy - rs) % G::RING][b] = exact_h<C, A, N, D>(p, in_frame, gy, obyte0 + b);
-                }
-                if (p.strict_counter && tid == 0) atomicAdd(p.strict_counter, (unsigned long long)(4 * sm.hcount));
-                __syncthreads();
-                if (tid == 0) sm.hcount = 0;
-            }
-        }
         // the input stage is free again: prefetch chunk+2 into it
         if (tid == 0 && chunk + 2 < nchunks) issue(chunk + 2);
 
         // ------------------------------ V pass ------------------------------
         if (v_active) {
-            uint8_t *ocol = out_frame + obyte0 + 4 * tid;
 #pragma unroll 1
-            for (int lb = 0; lb < G::RB; lb += TAPS) {
+            for (int sub = 0; sub < G::RB / G::UNR; sub++) {
+                // rows rb..rb+UNR-1 arrive; row r completes the outputs y with floor(y*D/N) = r - A.
+                // rb - A = D*t0 + S0 exactly, so everything relative to ybase = N*t0 is static.
+                const int rb = r0 + sub * G::UNR;
+                const int slotb = slot0 + sub * G::UNR;
+                const int t0 = (rb - A - G::S0) / D;               // exact division (also for negative values)
+                const int ybase = N * t0;
+                uint8_t *obase = ocol + (long long)(ybase - p.out_row0) * opitch;
+                unsigned long long fixmask = 0;                    // bit yy: output row ybase+yy needs exact recomputation
+                const bool interior = (ybase >= ys) && (ybase + G::YSPAN <= ye);
+                auto body = [&](auto check_tag) {
+                    constexpr bool CHECK = decltype(check_tag)::value;
 #pragma unroll
-            for (int j = 0; j < TAPS; j++) {                   // j = static window slot of the new row
-                const int r = r0 + lb + j;
-                const uint32_t w = *reinterpret_cast<const uint32_t *>(&sm.ring[(r - rs) % G::RING][4 * tid]);
-                word_to_f32x4(w, win[j][0], win[j][1], win[j][2], win[j][3]);
-                const int m = r - A;                           // floor(y*D/N) of the rows that complete now
-                if (m < D * pv0) continue;
-                const int y_lo = (m * N + D - 1) / D, y_hi = min(((m + 1) * N + D - 1) / D, ye);
-#pragma unroll 1
-                for (int y = max(y_lo, ys); y < y_hi; y++) {
-                    const int ph = (y * D) % N;
-                    uint32_t q;
-                    bool fix = false;
-                    if (ph == 0 && p.exact_y) {
-                        // phase 0: the centre tap (window row m) is the result
-                        q = *reinterpret_cast<const uint32_t *>(&sm.ring[(m - rs) % G::RING][4 * tid]);
-                        if (p.strict_v_identity) {
-                            float z[4];
+                    for (int lr = 0; lr < G::UNR; lr++) {
+                        const int j = lr % TAPS;                    // static window slot of the new row
+                        const uint32_t w = *reinterpret_cast<const uint32_t *>(vcol + ((slotb + lr) & RMASK) * F_SW_MAX);
+                        word_to_f32x4(w, win[j][0], win[j][1], win[j][2], win[j][3]);
+                        const int s = (G::S0 + lr) % D, tq = (G::S0 + lr) / D;     // r - A = D*(t0+tq) + s
+                        const int yfirst = N * tq + cdiv_c(s * N, D), ylast = N * tq + cdiv_c((s + 1) * N, D);
 #pragma unroll
-                            for (int e = 0; e < 4; e++) z[e] = win[(j + 1 + (A - 1)) % TAPS][e];
-                            bool dark = false;
+                        for (int yy = yfirst; yy < ylast; yy++) {
+                            const int ph = (yy * D) % N;
+                            if (CHECK && (ybase + yy < ys || ybase + yy >= ye)) continue;
+                            uint32_t q;
+                            if (ph == 0) {
+                                // phase 0: the centre tap (row r - A) is the result; flag it unless the
+                                // "cannot flip" filter of plan.cpp proves the reference returns it too
+                                q = *reinterpret_cast<const uint32_t *>(vcol + ((slotb + lr - A) & RMASK) * F_SW_MAX);
+                                uint32_t zor = v_force;
 #pragma unroll
-                            for (int k = 0; k < TAPS; k++) {
-                                if (!((KM >> k) & 1)) continue;
-                                const float kk = -p.align_k[k];
+                                for (int e = 0; e < 4; e++) {
+                                    float z = win[(j + 1 + (A - 1)) % TAPS][e];
 #pragma unroll
-                                for (int e = 0; e < 4; e++) z[e] = fmaf(win[(j + 1 + k) % TAPS][e], kk, z[e]);
+                                    for (int k = 0; k < TAPS; k++)
+                                        if ((KM >> k) & 1) z = fmaf(win[(j + 1 + k) % TAPS][e], -p.align_k[k], z);
+                                    zor |= __float_as_uint(z);
+                                }
+                                if (zor & v_signmask) fixmask |= 1ull << yy;
+                            } else {
+                                float xa[4];
+#pragma unroll
+                                for (int e = 0; e < 4; e++) xa[e] = -guard;
+#pragma unroll
+                                for (int k = 0; k < TAPS; k++)
+#pragma unroll
+                                    for (int e = 0; e < 4; e++) xa[e] = fmaf(win[(j + 1 + k) % TAPS][e], p.wtab[ph * 8 + k], xa[e]);
+                                q = quantise4(xa[0], xa[1], xa[2], xa[3]);
+                                const uint32_t qb = quantise4(xa[0] + g2, xa[1] + g2, xa[2] + g2, xa[3] + g2);
+                                if (q != qb) fixmask |= 1ull << yy;
                             }
-#pragma unroll
-                            for (int e = 0; e < 4; e++) dark |= (z[e] < 0.02f) && (win[(j + 1 + (A - 1)) % TAPS][e] > 0.5f);
-                            fix = dark;
-                        }
-                    } else {
-                        const float4 wlo = *reinterpret_cast<const float4 *>(&sm.wv[ph][0]);
-                        const float4 whi = *reinterpret_cast<const float4 *>(&sm.wv[ph][4]);
-                        const float wk[8] = {wlo.x, wlo.y, wlo.z, wlo.w, whi.x, whi.y, whi.z, whi.w};
-                        float xa[4], xb[4];
-#pragma unroll
-                        for (int e = 0; e < 4; e++) xa[e] = -p.guard;
-#pragma unroll
-                        for (int k = 0; k < TAPS; k++)
-#pragma unroll
-                            for (int e = 0; e < 4; e++) xa[e] = fmaf(win[(j + 1 + k) % TAPS][e], wk[k], xa[e]);
-#pragma unroll
-                        for (int e = 0; e < 4; e++) xb[e] = xa[e] + g2;
-                        q = quantise4(xa[0], xa[1], xa[2], xa[3]);
-                        fix = q != quantise4(xb[0], xb[1], xb[2], xb[3]);
-                    }
-                    *reinterpret_cast<uint32_t *>(ocol + (long long)(y - p.out_row0) * p.out_pitch) = q;
-                    if (fix) {
-                        const int pos = atomicAdd(&sm.vcount, 1);
-                        if (pos < F_LIST) {
-                            sm.vlist[pos] = ((uint32_t)(y - ys) << 16) | (uint32_t)(4 * tid);
-                        } else {                               // list full: recompute in place
-                            for (int e = 0; e < 4; e++)
-                                ocol[(long long)(y - p.out_row0) * p.out_pitch + e] = exact_v<TAPS, G::RING>(
-                                    sm.ring, p.wdy + (long long)y * TAPS, m - A + 1 - rs, 4 * tid + e);
+                            *reinterpret_cast<uint32_t *>(obase + (long long)yy * opitch) = q;
                         }
                     }
+                };
+                if (interior) body(std::false_type{}); else body(std::true_type{});
+                while (fixmask) {                                   // rare: exact recomputation of one output word
+                    const int yy = __ffsll((long long)fixmask) - 1;
+                    fixmask &= fixmask - 1;
+                    const int y = ybase + yy;
+                    const int first = (y * D) / N - A + 1;          // first tap row (full_TB.h:72)
+                    const int ph = (y * D) % N;
+                    const double *w = (p.uniform_y && N <= 8) ? &p.wdtab[ph * 8] : p.wdy + (long long)y * TAPS;
+                    uint32_t q = 0;
+#pragma unroll 1
+                    for (int e = 0; e < 4; e++) {
+                        double sum = 0.0;                           // full_TB.h:71-75 on the uint8 intermediate rows
+#pragma unroll
+                        for (int k = 0; k < TAPS; k++) {
+                            const uint8_t v = vcol[((first + k - rs) & RMASK) * F_SW_MAX + e];
+                            sum = __dadd_rn(sum, __dmul_rn((double)v, w[k]));
+                        }
+                        q |= (uint32_t)quantise_f64(sum) << (8 * e);
+                    }
+                    *reinterpret_cast<uint32_t *>(obase + (long long)yy * opitch) = q;
+                    n_strict += 4;
                 }
             }
-            }
         }
-        __syncthreads();
-        {   // deferred exact V samples (full_TB.h:71-75 arithmetic on the uint8 intermediate rows)
-            const int n = min(sm.vcount, F_LIST);
-            if (n > 0) {
-                for (int i = tid; i < 4 * n; i += F_THREADS) {
-                    const uint32_t entry = sm.vlist[i >> 2];
-                    const int y = ys + (int)(entry >> 16), b = (int)(entry & 0xffff) + (i & 3);
-                    const int first = (int)(((long long)y * D) / N) - A + 1;
-                    out_frame[(long long)(y - p.out_row0) * p.out_pitch + obyte0 + b] =
-                        exact_v<TAPS, G::RING>(sm.ring, p.wdy + (long long)y * TAPS, first - rs, b);
-                }
-                if (p.strict_counter && tid == 0) atomicAdd(p.strict_counter, (unsigned long long)(4 * sm.vcount));
-                __syncthreads();
-                if (tid == 0) sm.vcount = 0;
-                __syncthreads();
-            }
-        }
+        // no barrier here: RING >= 2*RB + TAPS keeps the rows this chunk's V pass reads intact while the
+        // next chunk's H pass writes; the barrier after that H pass orders everything else.
     }
+    if (p.strict_counter && n_strict) atomicAdd(p.strict_counter, n_strict);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -447,7 +428,7 @@ EncodeFn get_encode() {
 }
 
 template <int C, int A, int N, int D, int PH, int KM>
-int launch_one(const KParams &k, const float *phase_w, const float *align_k, int exact_x, int exact_y, cudaStream_t s) {
+int launch_one(const KParams &k, const FastHostTables &t, cudaStream_t s) {
     using G = Geo<C, A, N, D, PH>;
     EncodeFn encode = get_encode();
     if (!encode) return -1;
@@ -496,11 +477,14 @@ int launch_one(const KParams &k, const float *phase_w, const float *align_k, int
     p.out_row0 = k.out_row0; p.out_rows = k.out_rows; p.in_row0 = k.in_row0; p.in_rows = k.in_rows;
     p.sw = sw; p.groups = best_groups; p.seg_periods = seg_periods; p.vperiod0 = vperiod0;
     p.wdx = k.wdx; p.wdy = k.wdy; p.guard = k.guard;
-    p.exact_x = exact_x; p.exact_y = exact_y;
+    p.exact_x = t.exact_x; p.exact_y = t.exact_y;
+    p.uniform_x = t.uniform_x; p.uniform_y = t.uniform_y;
     p.strict_v_identity = (k.flags & LANCZOS_FLAG_FAST_ALIGNED) ? 0 : 1;
-    for (int i = 0; i < 8; i++) p.align_k[i] = i < 2 * A ? align_k[i] : 0.f;
+    for (int i = 0; i < 8; i++) p.align_k[i] = i < 2 * A ? t.align_k[i] : 0.f;
     for (int ph = 0; ph < N; ph++)
-        for (int t = 0; t < 8; t++) p.wtab[ph * 8 + t] = t < 2 * A ? phase_w[ph * 2 * A + t] : 0.f;
+        for (int q = 0; q < 8; q++) p.wtab[ph * 8 + q] = q < 2 * A ? t.phase_w[ph * 2 * A + q] : 0.f;
+    for (int ph = 0; ph < N && ph < 8; ph++)
+        for (int q = 0; q < 8; q++) p.wdtab[ph * 8 + q] = q < 2 * A ? t.phase_wd[ph * 2 * A + q] : 0.0;
     p.strict_counter = k.strict_counter;
 
     auto kern = lanczos_fast_kernel<C, A, N, D, PH, KM>;
@@ -518,8 +502,7 @@ int launch_one(const KParams &k, const float *phase_w, const float *align_k, int
 }  // namespace
 
 // Returns 0 on launch, >0 cudaError, -1 when no specialised kernel applies (caller falls back).
-int launch_fast(const KParams &k, const float *phase_w_host, const float *align_k_host, int exact_x, int exact_y,
-                int *kernel_id, cudaStream_t s) {
+int launch_fast(const KParams &k, const FastHostTables &t, int *kernel_id, cudaStream_t s) {
     // layout requirements of the TMA map and of the 32-bit/128-bit accesses
     if ((k.in_w * k.channels) % 4 != 0 || (k.out_w * k.channels) % 4 != 0) return -1;
     if (k.in_pitch % 16 != 0 || k.out_pitch % 4 != 0) return -1;
@@ -529,12 +512,12 @@ int launch_fast(const KParams &k, const float *phase_w_host, const float *align_
     const int C = k.channels, A = k.a, N = k.scale_n, D = k.scale_d;
     // KM: taps whose phase-0 residue is negative (nonzero filter constant); the host table must agree
     int km = 0;
-    for (int t = 0; t < 2 * A; t++)
-        if (align_k_host[t] != 0.f) km |= 1 << t;
+    for (int q = 0; q < 2 * A; q++)
+        if (t.align_k[q] != 0.f) km |= 1 << q;
 #define LZ_CASE(c, a, n, d, ph, kmask, id)                                                             \
     if (C == c && A == a && N == n && D == d && (km & ~(kmask)) == 0) {                                 \
         *kernel_id = id;                                                                                \
-        return launch_one<c, a, n, d, ph, kmask>(k, phase_w_host, align_k_host, exact_x, exact_y, s);   \
+        return launch_one<c, a, n, d, ph, kmask>(k, t, s);                                              \
     }
     // a = 3: sin(2*pi) < 0 in double, so the |d| = 2 taps (k = 0 and k = 4) carry negative residues
     LZ_CASE(3, 3, 2, 1, 8, 0x11, 1)

@@ -58,7 +58,7 @@ int resolve_desc(const lanczos_desc *in, lanczos_desc *out) {
 }
 
 static int build_axis(AxisTables &t, int out_len, int in_len, int a, int n, int dd,
-                      const std::vector<float> &phase_w) {
+                      const std::vector<float> &phase_w, const std::vector<double> &phase_wd) {
     const int taps = 2 * a;
     const double scale = (double)n / dd;  // lanczos.h:112
     t.out_len = out_len;
@@ -67,6 +67,7 @@ static int build_axis(AxisTables &t, int out_len, int in_len, int a, int n, int 
     t.wd.assign((size_t)out_len * taps, 0.0);
     t.wf.assign((size_t)out_len * taps, 0.f);
     t.aligned_exact = true;
+    t.uniform_phase = true;
     t.fast_err = 0;
     const double u = std::ldexp(1.0, -24);  // relative half-ulp of fp32
     for (int xx = 0; xx < out_len; xx++) {
@@ -84,6 +85,7 @@ static int build_axis(AxisTables &t, int out_len, int in_len, int a, int n, int 
             const double w = ref_kernel(x - i, a);  // full_TB.h:60
             const float wf = (float)w;
             t.wd[(size_t)xx * taps + k] = w;
+            if (w != phase_wd[(size_t)phase * taps + k]) t.uniform_phase = false;
             t.wf[(size_t)xx * taps + k] = wf;
             werr_coord += 255.0 * std::fabs((double)wf - w);
             werr_phase += 255.0 * std::fabs((double)phase_w[(size_t)phase * taps + k] - w);
@@ -135,9 +137,9 @@ int build_plan(const lanczos_desc *desc, Plan *out) {
             if (K > 1e-7) p.align_k[k] = (float)(K * (1.0 + 1e-6));
         }
     }
-    rc = build_axis(p.x, p.d.out_w, p.d.in_w, a, n, dd, p.phase_w);
+    rc = build_axis(p.x, p.d.out_w, p.d.in_w, a, n, dd, p.phase_w, p.phase_wd);
     if (rc != LANCZOS_OK) return rc;
-    rc = build_axis(p.y, p.d.out_h, p.d.in_h, a, n, dd, p.phase_w);
+    rc = build_axis(p.y, p.d.out_h, p.d.in_h, a, n, dd, p.phase_w, p.phase_wd);
     if (rc != LANCZOS_OK) return rc;
     // guard band: twice the rigorous fp32 error bound, never below 2^-13
     const double e = std::max(p.x.fast_err, p.y.fast_err);

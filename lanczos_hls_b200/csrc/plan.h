@@ -23,6 +23,7 @@ struct AxisTables {
     std::vector<double> wd;   // [out_len][2a] L(x-(i0+k)) exactly as full_TB.h:60 evaluates it
     std::vector<float> wf;    // [out_len][2a] the same rounded to float (fast path)
     bool aligned_exact = true;  // every phase-0 coordinate has x exactly integral in double
+    bool uniform_phase = true;  // wd[xx][k] == phase_wd[phase(xx)][k] bit for bit, for every coordinate
     double fast_err = 0;        // rigorous bound on |fp32 fast sum - reference double sum|
 };
 
