@@ -36,8 +36,6 @@ namespace lzb {
 
 namespace {
 
-constexpr int F_THREADS = 256;
-constexpr int F_SW_MAX = 1024;   // strip width in output bytes (one 32-bit word per V thread)
 
 // ---------------------------------------------------------------------------------------------
 // PTX helpers
@@ -69,22 +67,24 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
         : "memory");
 }
 
-// two bytes of `w` (selected by SEL, e.g. 0x7170 = bytes 0 and 1) as a pair of fp16 values 1024+b
-template <uint32_t SEL>
-__device__ __forceinline__ uint32_t bytes_to_h2(uint32_t w) { return __byte_perm(w, 0x64006400u, SEL); }
-// fp32 = fp16 (low/high half of h2) - 1024 : one FHADD each, exact
+// u8 -> fp32 without the 16/clk I2F unit: PRMT places two bytes into the low bytes of two fp16
+// lanes (0x00bb = the fp16 SUBNORMAL b * 2^-24), and one FHADD per byte widens it to fp32 exactly.
+// All fp32 pixel values in these kernels therefore carry a factor 2^-24 (kPixScale); the float
+// weight tables are pre-multiplied by 2^24 on the host (exact, powers of two), so sums come out in
+// pixel units with exactly the rounding they would have unscaled.
+constexpr float kPixUnscale = 16777216.f;  // 2^24
 __device__ __forceinline__ float h2_lo_to_f32(uint32_t h2) {
     float f;
-    asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tadd.rn.f32.f16 %0, lo, %2;\n\t}" : "=f"(f) : "r"(h2), "f"(-1024.f));
+    asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tadd.rn.f32.f16 %0, lo, 0f00000000;\n\t}" : "=f"(f) : "r"(h2));
     return f;
 }
 __device__ __forceinline__ float h2_hi_to_f32(uint32_t h2) {
     float f;
-    asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tadd.rn.f32.f16 %0, hi, %2;\n\t}" : "=f"(f) : "r"(h2), "f"(-1024.f));
+    asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tadd.rn.f32.f16 %0, hi, 0f00000000;\n\t}" : "=f"(f) : "r"(h2));
     return f;
 }
 __device__ __forceinline__ void word_to_f32x4(uint32_t w, float &f0, float &f1, float &f2, float &f3) {
-    const uint32_t a = bytes_to_h2<0x7170>(w), b = bytes_to_h2<0x7372>(w);
+    const uint32_t a = __byte_perm(w, 0u, 0x4140), b = __byte_perm(w, 0u, 0x4342);
     f0 = h2_lo_to_f32(a); f1 = h2_hi_to_f32(a); f2 = h2_lo_to_f32(b); f3 = h2_hi_to_f32(b);
 }
 
@@ -122,8 +122,10 @@ struct FastParams {
     unsigned long long *strict_counter;
 };
 
-template <int C, int A, int N, int D, int PH>
+template <int C, int A, int N, int D, int PH, int NT>
 struct Geo {
+    static constexpr int THREADS = NT;
+    static constexpr int SW_MAX = 4 * NT;       // strip width in output bytes (one 32-bit word per V thread)
     static constexpr int TAPS = 2 * A;
     static constexpr int IN_B = PH * D * C;     // input bytes owned by one H item
     static constexpr int OUT_B = PH * N * C;    // output bytes produced by one H item
@@ -135,10 +137,10 @@ struct Geo {
     static constexpr int MIS = (PAD_L - HALO_L) % 4;              // window start inside its first word
     static constexpr int WIN0 = PAD_L - HALO_L - MIS;             // first word (byte offset) for group 0
     static constexpr int NWORDS = (MIS + WIN_B + 3) / 4;
-    static constexpr int MAX_GROUPS = F_SW_MAX / OUT_B;
+    static constexpr int MAX_GROUPS = SW_MAX / OUT_B;
     static constexpr int BOX_B = 16 * ((PAD_L + MAX_GROUPS * IN_B + HALO_R + 15) / 16);  // TMA box row bytes
     static constexpr int RB = 12;                                 // input rows per chunk
-    static constexpr int RING = 32;                               // intermediate rows kept in smem (power of 2)
+    static constexpr int RING = 3 * RB;                           // intermediate rows kept in smem
     static constexpr int STAGE_B = 128 * ((RB * BOX_B + 127) / 128);  // TMA destinations must be 128-byte aligned
     // the first row pushed by a segment is rs = D*pv0 - A + 1, so (row - A) mod D is static per chunk row
     static constexpr int S0 = (((1 - 2 * A) % D) + D) % D;
@@ -147,16 +149,17 @@ struct Geo {
     static_assert(IN_B % 4 == 0, "H item input must be word aligned");
     static_assert(OUT_B % 16 == 0, "H item output must be 16-byte aligned");
     static_assert(RB % UNR == 0, "chunk must be a multiple of the unrolled V block");
-    static_assert(RING >= 2 * RB + TAPS, "ring too small for barrier-free V/H overlap");
+    static_assert(RING >= 2 * RB + TAPS && RING % RB == 0, "ring too small for barrier-free V/H overlap");
     static_assert(BOX_B / 4 <= 256, "TMA box too wide");
     static_assert(N <= 32, "phase table too large for kernel params");
-    static_assert(YSPAN <= 64, "fix mask too small");
+    static_assert(YSPAN <= 16, "fix mask (4 bits per output row) too small");
+    static_assert(OUT_B / 4 <= 16, "fix mask (4 bits per output word) too small");
 };
 
 template <class G>
 struct __align__(128) FastSmem {
     uint8_t in[2][G::STAGE_B];            // TMA destinations (double buffered), row lr at lr * BOX_B
-    uint8_t ring[G::RING][F_SW_MAX];      // H-pass results (uint8), row r lives in slot (r - rs) & (RING-1)
+    uint8_t ring[G::RING][G::SW_MAX];     // H-pass results (uint8), row r lives in slot (r - rs) % RING
     unsigned long long bar[2];
 };
 
@@ -172,12 +175,12 @@ __device__ __noinline__ uint8_t exact_taps(const uint8_t *tap0, int stride, cons
     return quantise_f64(sum);
 }
 
-template <int C, int A, int N, int D, int PH, int KM>
-__global__ void __launch_bounds__(F_THREADS, 2)
+template <int C, int A, int N, int D, int PH, int KM, int NT>
+__global__ void __launch_bounds__(NT, (NT == 128 ? 5 : 2))
 lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ FastParams p) {
-    using G = Geo<C, A, N, D, PH>;
+    using G = Geo<C, A, N, D, PH, NT>;
     constexpr int TAPS = G::TAPS;
-    constexpr int RMASK = G::RING - 1;
+    constexpr int SWM = G::SW_MAX;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     FastSmem<G> &sm = *reinterpret_cast<FastSmem<G> *>(smem_raw);
 
@@ -221,20 +224,23 @@ lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
         if (nchunks > 1) issue(1);
     }
 
-    // V-pass state: the last TAPS intermediate rows of this thread's word column, as fp32
-    float win[TAPS][4];
+    // V-pass state: the last TAPS intermediate rows of this thread's word column, as fp32 pairs
+    // (value * 2^-24), plus the raw words (phase-0 rows are copies of the centre tap)
+    float2 win[TAPS][2];
+    uint32_t raw[TAPS];
 #pragma unroll
-    for (int j = 0; j < TAPS; j++)
-#pragma unroll
-        for (int e = 0; e < 4; e++) win[j][e] = 0.f;
+    for (int j = 0; j < TAPS; j++) {
+        win[j][0] = win[j][1] = make_float2(0.f, 0.f);
+        raw[j] = 0;
+    }
     const bool v_active = 4 * tid < valid_bytes;
     const float guard = p.guard, g2 = 2.f * p.guard;
     const long long opitch = p.out_pitch;
     const uint8_t *vcol = &sm.ring[0][4 * tid];               // this thread's word column of the ring
     uint8_t *ocol = out_frame + obyte0 + 4 * tid;
     unsigned long long n_strict = 0;
-    // flag handling without loop-invariant branches (they would triple the unrolled code):
-    //   v_force   sign bit set  -> every phase-0 row is recomputed (inexact alignment, e.g. 17/10)
+    // flag handling without loop-invariant branches (they would multiply the unrolled code):
+    //   *_force    sign bit set -> every phase-0 sample is recomputed (inexact alignment, e.g. 17/10)
     //   v_signmask 0            -> phase-0 rows are never recomputed (LANCZOS_FLAG_FAST_ALIGNED)
     const uint32_t v_force = p.exact_y ? 0u : 0x80000000u;
     const uint32_t v_signmask = (p.exact_y && !p.strict_v_identity) ? 0u : 0x80000000u;
@@ -243,11 +249,10 @@ lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
     for (int chunk = 0; chunk < nchunks; chunk++) {
         const int st = chunk & 1;
         mbar_wait(st ? bar1 : bar0, (chunk >> 1) & 1);
-        const int r0 = rs + chunk * G::RB;                    // first row of this chunk
-        const int slot0 = (chunk * G::RB) & RMASK;            // ring slot of row r0
+        const int slot0 = (chunk % (G::RING / G::RB)) * G::RB;   // ring slot of this chunk's first row (no wrap inside)
 
         // ------------------------------ H pass ------------------------------
-        for (int item = tid; item < G::RB * groups; item += F_THREADS) {
+        for (int item = tid; item < G::RB * groups; item += NT) {
             const int lr = item / groups, g = item - lr * groups;
             const uint8_t *srow = &sm.in[st][lr * G::BOX_B];
             const uint32_t *src = reinterpret_cast<const uint32_t *>(srow + G::WIN0 + g * G::IN_B);
@@ -255,14 +260,14 @@ lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
 #pragma unroll
             for (int wi = 0; wi < G::NWORDS; wi++)
                 word_to_f32x4(src[wi], f[4 * wi], f[4 * wi + 1], f[4 * wi + 2], f[4 * wi + 3]);
-            // window byte k (k = 0 is HALO_L bytes left of the item's own input) = f[MIS + k]
+            // window byte k (k = 0 is HALO_L bytes left of the item's own input) = f[MIS + k] * 2^24
             uint32_t outw[G::OUT_B / 4];
-            uint32_t need_fix = 0;        // bit per output word
+            unsigned long long fixbytes = 0;   // 4 bits per output word: bytes to recompute exactly
 #pragma unroll
             for (int ow = 0; ow < G::OUT_B / 4; ow++) {
                 float xa[4], xb[4];
                 uint32_t zor = 0;          // sign bit set <=> some phase-0 sample may flip (or must be recomputed)
-                bool has_p0 = false;
+                uint32_t p0mask = 0;       // which bytes of the word are phase-0 samples (static)
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
                     const int o = 4 * ow + e;              // output byte of the item
@@ -272,14 +277,13 @@ lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                     const int base = (per * D + (r * D) / N) * C + c;   // window index of tap 0
                     if (ph == 0) {
                         const float v = f[G::MIS + base + (A - 1) * C];
-                        xa[e] = v;
-                        xb[e] = v;
+                        xa[e] = xb[e] = v * kPixUnscale;
                         float z = v;                        // "cannot flip" filter of plan.cpp: z >= 0 -> output is v
 #pragma unroll
                         for (int k = 0; k < TAPS; k++)
                             if ((KM >> k) & 1) z = fmaf(f[G::MIS + base + k * C], -p.align_k[k], z);
                         zor |= __float_as_uint(z);
-                        has_p0 = true;
+                        p0mask |= 1u << e;
                     } else {
                         float acc = -guard;
 #pragma unroll
@@ -291,28 +295,30 @@ lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                 const uint32_t qa = quantise4(xa[0], xa[1], xa[2], xa[3]);
                 const uint32_t qb = quantise4(xb[0], xb[1], xb[2], xb[3]);
                 outw[ow] = qa;
-                if (has_p0) zor |= h_force;                  // inexact alignment: phase-0 samples always recomputed
-                if (((qa ^ qb) | (zor & 0x80000000u)) != 0) need_fix |= 1u << ow;
+                if (p0mask) zor |= h_force;                  // inexact alignment: phase-0 samples always recomputed
+                const uint32_t d = qa ^ qb;
+                if ((d | (zor & 0x80000000u)) != 0) {        // rare
+                    uint32_t m4 = (zor & 0x80000000u) ? p0mask : 0u;
+                    m4 |= ((d & 0xffu) ? 1u : 0u) | ((d & 0xff00u) ? 2u : 0u) | ((d & 0xff0000u) ? 4u : 0u) | ((d & 0xff000000u) ? 8u : 0u);
+                    fixbytes |= (unsigned long long)m4 << (4 * ow);
+                }
             }
-            uint8_t *drow = &sm.ring[(slot0 + lr) & RMASK][g * G::OUT_B];
+            uint8_t *drow = &sm.ring[slot0 + lr][g * G::OUT_B];
             uint4 *dst = reinterpret_cast<uint4 *>(drow);
 #pragma unroll
             for (int v4 = 0; v4 < G::OUT_B / 16; v4++)
                 dst[v4] = make_uint4(outw[4 * v4], outw[4 * v4 + 1], outw[4 * v4 + 2], outw[4 * v4 + 3]);
-            while (need_fix) {                               // rare: exact recomputation of one output word
-                const int ow = __ffs(need_fix) - 1;
-                need_fix &= need_fix - 1;
-                if (g * G::OUT_B + 4 * ow >= valid_bytes) continue;
-#pragma unroll 1
-                for (int e = 0; e < 4; e++) {
-                    const int ob = obyte0 + g * G::OUT_B + 4 * ow + e;   // global output byte column
-                    const int xx = ob / C, c = ob - xx * C;
-                    const int first = (xx * D) / N - A + 1;                // first tap pixel (full_TB.h:59)
-                    const int ph = (xx * D) % N;
-                    const double *w = (p.uniform_x && N <= 8) ? &p.wdtab[ph * 8] : p.wdx + (long long)xx * TAPS;
-                    drow[4 * ow + e] = exact_taps<TAPS>(srow + G::PAD_L + first * C + c - ibyte0, C, w);
-                }
-                n_strict += 4;
+            while (fixbytes) {                               // rare: exact recomputation of one output byte
+                const int b = __ffsll((long long)fixbytes) - 1;
+                fixbytes &= fixbytes - 1;
+                if (g * G::OUT_B + b >= valid_bytes) continue;
+                const int ob = obyte0 + g * G::OUT_B + b;                // global output byte column
+                const int xx = ob / C, c = ob - xx * C;
+                const int first = (xx * D) / N - A + 1;                    // first tap pixel (full_TB.h:59)
+                const int ph = (xx * D) % N;
+                const double *w = (p.uniform_x && N <= 8) ? &p.wdtab[ph * 8] : p.wdx + (long long)xx * TAPS;
+                drow[b] = exact_taps<TAPS>(srow + G::PAD_L + first * C + c - ibyte0, C, w);
+                n_strict++;
             }
         }
         __syncthreads();
@@ -321,24 +327,26 @@ lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
 
         // ------------------------------ V pass ------------------------------
         if (v_active) {
+            const int r0 = rs + chunk * G::RB;                    // first row of this chunk
 #pragma unroll 1
             for (int sub = 0; sub < G::RB / G::UNR; sub++) {
                 // rows rb..rb+UNR-1 arrive; row r completes the outputs y with floor(y*D/N) = r - A.
                 // rb - A = D*t0 + S0 exactly, so everything relative to ybase = N*t0 is static.
                 const int rb = r0 + sub * G::UNR;
-                const int slotb = slot0 + sub * G::UNR;
+                const uint8_t *vrow = vcol + (slot0 + sub * G::UNR) * SWM;   // no ring wrap inside a block
                 const int t0 = (rb - A - G::S0) / D;               // exact division (also for negative values)
                 const int ybase = N * t0;
                 uint8_t *obase = ocol + (long long)(ybase - p.out_row0) * opitch;
-                unsigned long long fixmask = 0;                    // bit yy: output row ybase+yy needs exact recomputation
+                unsigned long long fixmask = 0;                    // 4 bits per output row: bytes to recompute exactly
                 const bool interior = (ybase >= ys) && (ybase + G::YSPAN <= ye);
                 auto body = [&](auto check_tag) {
                     constexpr bool CHECK = decltype(check_tag)::value;
 #pragma unroll
                     for (int lr = 0; lr < G::UNR; lr++) {
                         const int j = lr % TAPS;                    // static window slot of the new row
-                        const uint32_t w = *reinterpret_cast<const uint32_t *>(vcol + ((slotb + lr) & RMASK) * F_SW_MAX);
-                        word_to_f32x4(w, win[j][0], win[j][1], win[j][2], win[j][3]);
+                        const uint32_t w = *reinterpret_cast<const uint32_t *>(vrow + lr * SWM);
+                        raw[j] = w;
+                        word_to_f32x4(w, win[j][0].x, win[j][0].y, win[j][1].x, win[j][1].y);
                         const int s = (G::S0 + lr) % D, tq = (G::S0 + lr) / D;     // r - A = D*(t0+tq) + s
                         const int yfirst = N * tq + cdiv_c(s * N, D), ylast = N * tq + cdiv_c((s + 1) * N, D);
 #pragma unroll
@@ -349,54 +357,57 @@ lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                             if (ph == 0) {
                                 // phase 0: the centre tap (row r - A) is the result; flag it unless the
                                 // "cannot flip" filter of plan.cpp proves the reference returns it too
-                                q = *reinterpret_cast<const uint32_t *>(vcol + ((slotb + lr - A) & RMASK) * F_SW_MAX);
-                                uint32_t zor = v_force;
-#pragma unroll
-                                for (int e = 0; e < 4; e++) {
-                                    float z = win[(j + 1 + (A - 1)) % TAPS][e];
-#pragma unroll
-                                    for (int k = 0; k < TAPS; k++)
-                                        if ((KM >> k) & 1) z = fmaf(win[(j + 1 + k) % TAPS][e], -p.align_k[k], z);
-                                    zor |= __float_as_uint(z);
-                                }
-                                if (zor & v_signmask) fixmask |= 1ull << yy;
-                            } else {
-                                float xa[4];
-#pragma unroll
-                                for (int e = 0; e < 4; e++) xa[e] = -guard;
+                                q = raw[(j + 1 + (A - 1)) % TAPS];
+                                float2 z0 = win[(j + 1 + (A - 1)) % TAPS][0], z1 = win[(j + 1 + (A - 1)) % TAPS][1];
 #pragma unroll
                                 for (int k = 0; k < TAPS; k++)
+                                    if ((KM >> k) & 1) {
+                                        const float2 kk = make_float2(-p.align_k[k], -p.align_k[k]);
+                                        z0 = __ffma2_rn(win[(j + 1 + k) % TAPS][0], kk, z0);
+                                        z1 = __ffma2_rn(win[(j + 1 + k) % TAPS][1], kk, z1);
+                                    }
+                                const uint32_t zor = v_force | __float_as_uint(z0.x) | __float_as_uint(z0.y) |
+                                                     __float_as_uint(z1.x) | __float_as_uint(z1.y);
+                                if (zor & v_signmask) fixmask |= 15ull << (4 * yy);
+                            } else {
+                                float2 a0 = make_float2(-guard, -guard), a1 = a0;
 #pragma unroll
-                                    for (int e = 0; e < 4; e++) xa[e] = fmaf(win[(j + 1 + k) % TAPS][e], p.wtab[ph * 8 + k], xa[e]);
-                                q = quantise4(xa[0], xa[1], xa[2], xa[3]);
-                                const uint32_t qb = quantise4(xa[0] + g2, xa[1] + g2, xa[2] + g2, xa[3] + g2);
-                                if (q != qb) fixmask |= 1ull << yy;
+                                for (int k = 0; k < TAPS; k++) {
+                                    const float2 wk = make_float2(p.wtab[ph * 8 + k], p.wtab[ph * 8 + k]);
+                                    a0 = __ffma2_rn(win[(j + 1 + k) % TAPS][0], wk, a0);
+                                    a1 = __ffma2_rn(win[(j + 1 + k) % TAPS][1], wk, a1);
+                                }
+                                const float2 gg = make_float2(g2, g2);
+                                const float2 b0 = __fadd2_rn(a0, gg), b1 = __fadd2_rn(a1, gg);
+                                q = quantise4(a0.x, a0.y, a1.x, a1.y);
+                                const uint32_t d = q ^ quantise4(b0.x, b0.y, b1.x, b1.y);
+                                if (d != 0) {                   // rare
+                                    const uint32_t m4 = ((d & 0xffu) ? 1u : 0u) | ((d & 0xff00u) ? 2u : 0u) |
+                                                        ((d & 0xff0000u) ? 4u : 0u) | ((d & 0xff000000u) ? 8u : 0u);
+                                    fixmask |= (unsigned long long)m4 << (4 * yy);
+                                }
                             }
                             *reinterpret_cast<uint32_t *>(obase + (long long)yy * opitch) = q;
                         }
                     }
                 };
                 if (interior) body(std::false_type{}); else body(std::true_type{});
-                while (fixmask) {                                   // rare: exact recomputation of one output word
-                    const int yy = __ffsll((long long)fixmask) - 1;
+                while (fixmask) {                                   // rare: exact recomputation of one output byte
+                    const int bit = __ffsll((long long)fixmask) - 1;
                     fixmask &= fixmask - 1;
+                    const int yy = bit >> 2, e = bit & 3;
                     const int y = ybase + yy;
                     const int first = (y * D) / N - A + 1;          // first tap row (full_TB.h:72)
                     const int ph = (y * D) % N;
                     const double *w = (p.uniform_y && N <= 8) ? &p.wdtab[ph * 8] : p.wdy + (long long)y * TAPS;
-                    uint32_t q = 0;
-#pragma unroll 1
-                    for (int e = 0; e < 4; e++) {
-                        double sum = 0.0;                           // full_TB.h:71-75 on the uint8 intermediate rows
+                    double sum = 0.0;                               // full_TB.h:71-75 on the uint8 intermediate rows
 #pragma unroll
-                        for (int k = 0; k < TAPS; k++) {
-                            const uint8_t v = vcol[((first + k - rs) & RMASK) * F_SW_MAX + e];
-                            sum = __dadd_rn(sum, __dmul_rn((double)v, w[k]));
-                        }
-                        q |= (uint32_t)quantise_f64(sum) << (8 * e);
+                    for (int k = 0; k < TAPS; k++) {
+                        const uint8_t v = vcol[((first + k - rs) % G::RING) * SWM + e];
+                        sum = __dadd_rn(sum, __dmul_rn((double)v, w[k]));
                     }
-                    *reinterpret_cast<uint32_t *>(obase + (long long)yy * opitch) = q;
-                    n_strict += 4;
+                    obase[(long long)yy * opitch + e] = quantise_f64(sum);
+                    n_strict++;
                 }
             }
         }
@@ -427,9 +438,9 @@ EncodeFn get_encode() {
     return fn;
 }
 
-template <int C, int A, int N, int D, int PH, int KM>
+template <int C, int A, int N, int D, int PH, int KM, int NT>
 int launch_one(const KParams &k, const FastHostTables &t, cudaStream_t s) {
-    using G = Geo<C, A, N, D, PH>;
+    using G = Geo<C, A, N, D, PH, NT>;
     EncodeFn encode = get_encode();
     if (!encode) return -1;
     const int row_bytes = k.out_w * C;
@@ -441,7 +452,7 @@ int launch_one(const KParams &k, const FastHostTables &t, cudaStream_t s) {
         if ((gr * G::IN_B) % 16 != 0) continue;
         const int sw_c = gr * G::OUT_B;
         const int strips_c = (row_bytes + sw_c - 1) / sw_c;
-        const double eff = (double)row_bytes / ((double)strips_c * F_SW_MAX);
+        const double eff = (double)row_bytes / ((double)strips_c * G::SW_MAX);
         if (eff > best_eff + 1e-9) { best_eff = eff; best_groups = gr; }
     }
     if (best_groups == 0) return -1;
@@ -454,7 +465,8 @@ int launch_one(const KParams &k, const FastHostTables &t, cudaStream_t s) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int min_periods = std::max(1, (4 * G::RB) / D);
-    int segs = (int)((8LL * 2 * sms + (long long)strips * k.n_frames - 1) / ((long long)strips * k.n_frames));
+    const int ctas_per_sm = NT == 128 ? 5 : 2;
+    int segs = (int)((8LL * ctas_per_sm * sms + (long long)strips * k.n_frames - 1) / ((long long)strips * k.n_frames));
     segs = std::max(1, std::min(segs, std::max(1, vperiods / min_periods)));
     int seg_periods = (vperiods + segs - 1) / segs;
     segs = (vperiods + seg_periods - 1) / seg_periods;
@@ -482,12 +494,12 @@ int launch_one(const KParams &k, const FastHostTables &t, cudaStream_t s) {
     p.strict_v_identity = (k.flags & LANCZOS_FLAG_FAST_ALIGNED) ? 0 : 1;
     for (int i = 0; i < 8; i++) p.align_k[i] = i < 2 * A ? t.align_k[i] : 0.f;
     for (int ph = 0; ph < N; ph++)
-        for (int q = 0; q < 8; q++) p.wtab[ph * 8 + q] = q < 2 * A ? t.phase_w[ph * 2 * A + q] : 0.f;
+        for (int q = 0; q < 8; q++) p.wtab[ph * 8 + q] = q < 2 * A ? t.phase_w[ph * 2 * A + q] * 16777216.f : 0.f;  // x 2^24, see kPixUnscale
     for (int ph = 0; ph < N && ph < 8; ph++)
         for (int q = 0; q < 8; q++) p.wdtab[ph * 8 + q] = q < 2 * A ? t.phase_wd[ph * 2 * A + q] : 0.0;
     p.strict_counter = k.strict_counter;
 
-    auto kern = lanczos_fast_kernel<C, A, N, D, PH, KM>;
+    auto kern = lanczos_fast_kernel<C, A, N, D, PH, KM, NT>;
     const size_t smem = sizeof(FastSmem<G>) + 128;
     static bool attr_set[64] = {};
     if (!attr_set[dev & 63]) {
@@ -495,7 +507,7 @@ int launch_one(const KParams &k, const FastHostTables &t, cudaStream_t s) {
         attr_set[dev & 63] = true;
     }
     dim3 grid(strips, segs, k.n_frames);
-    kern<<<grid, F_THREADS, smem, s>>>(map, p);
+    kern<<<grid, NT, smem, s>>>(map, p);
     return (int)cudaGetLastError();
 }
 
@@ -517,7 +529,7 @@ int launch_fast(const KParams &k, const FastHostTables &t, int *kernel_id, cudaS
 #define LZ_CASE(c, a, n, d, ph, kmask, id)                                                             \
     if (C == c && A == a && N == n && D == d && (km & ~(kmask)) == 0) {                                 \
         *kernel_id = id;                                                                                \
-        return launch_one<c, a, n, d, ph, kmask>(k, t, s);                                              \
+        return launch_one<c, a, n, d, ph, kmask, 128>(k, t, s);                                         \
     }
     // a = 3: sin(2*pi) < 0 in double, so the |d| = 2 taps (k = 0 and k = 4) carry negative residues
     LZ_CASE(3, 3, 2, 1, 8, 0x11, 1)

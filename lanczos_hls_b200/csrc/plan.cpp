@@ -79,7 +79,7 @@ static int build_axis(AxisTables &t, int out_len, int in_len, int a, int n, int 
         if (phase == 0 && x != fx) t.aligned_exact = false;
         const int first = (int)q - a + 1;
         t.i0[xx] = first;
-        double werr_coord = 0, werr_phase = 0, abs_sum = 0;
+        double werr_coord = 0, werr_phase = 0, abs_sum = 0, round_err = 0;
         for (int k = 0; k < taps; k++) {
             const int i = first + k;
             const double w = ref_kernel(x - i, a);  // full_TB.h:60
@@ -89,10 +89,11 @@ static int build_axis(AxisTables &t, int out_len, int in_len, int a, int n, int 
             t.wf[(size_t)xx * taps + k] = wf;
             werr_coord += 255.0 * std::fabs((double)wf - w);
             werr_phase += 255.0 * std::fabs((double)phase_w[(size_t)phase * taps + k] - w);
+            // taps are accumulated in ascending order (both kernels): the k-th FMA rounds a partial sum
+            // bounded by the prefix of absolute products (+1 covers the -guard start value)
             abs_sum += 255.0 * std::fabs(w);
+            round_err += u * (abs_sum + 1.0);
         }
-        // any summation order: each of the `taps` FMAs rounds a partial sum bounded by abs_sum
-        const double round_err = taps * u * (abs_sum + 1.0);
         t.fast_err = std::max(t.fast_err, std::max(werr_coord, werr_phase) + round_err);
     }
     return LANCZOS_OK;
@@ -141,9 +142,9 @@ int build_plan(const lanczos_desc *desc, Plan *out) {
     if (rc != LANCZOS_OK) return rc;
     rc = build_axis(p.y, p.d.out_h, p.d.in_h, a, n, dd, p.phase_w, p.phase_wd);
     if (rc != LANCZOS_OK) return rc;
-    // guard band: twice the rigorous fp32 error bound, never below 2^-13
+    // guard band: 1.25x the rigorous fp32 error bound, never below 2^-14
     const double e = std::max(p.x.fast_err, p.y.fast_err);
-    p.guard = (float)std::max(2.0 * e, std::ldexp(1.0, -13));
+    p.guard = (float)std::max(1.25 * e, std::ldexp(1.0, -14));
 
     // in-place aliasing of the vertical pass (full_TB.h:67-77): going bottom-up, row xx reads
     // rows first..last; any row i > xx has already been overwritten with final output.
