@@ -26,6 +26,7 @@
 // filter of plan.cpp and recomputed exactly when it fails.  Recomputations are deferred to
 // per-CTA lists so that they run 32 lanes wide.
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 #include <cuda.h>
 
@@ -152,8 +153,8 @@ struct Geo {
     static_assert(RING >= 2 * RB + TAPS && RING % RB == 0, "ring too small for barrier-free V/H overlap");
     static_assert(BOX_B / 4 <= 256, "TMA box too wide");
     static_assert(N <= 32, "phase table too large for kernel params");
-    static_assert(YSPAN <= 16, "fix mask (4 bits per output row) too small");
-    static_assert(OUT_B / 4 <= 16, "fix mask (4 bits per output word) too small");
+    static_assert(YSPAN <= 32, "fix mask (bit per output row) too small");
+    static_assert(OUT_B / 4 <= 32, "fix mask (bit per output word) too small");
 };
 
 template <class G>
@@ -176,7 +177,7 @@ __device__ __noinline__ uint8_t exact_taps(const uint8_t *tap0, int stride, cons
 }
 
 template <int C, int A, int N, int D, int PH, int KM, int NT>
-__global__ void __launch_bounds__(NT, (NT == 128 ? 5 : 2))
+__global__ void __launch_bounds__(NT, (NT == 128 ? 6 : 3))
 lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ FastParams p) {
     using G = Geo<C, A, N, D, PH, NT>;
     constexpr int TAPS = G::TAPS;
@@ -262,7 +263,7 @@ lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                 word_to_f32x4(src[wi], f[4 * wi], f[4 * wi + 1], f[4 * wi + 2], f[4 * wi + 3]);
             // window byte k (k = 0 is HALO_L bytes left of the item's own input) = f[MIS + k] * 2^24
             uint32_t outw[G::OUT_B / 4];
-            unsigned long long fixbytes = 0;   // 4 bits per output word: bytes to recompute exactly
+            uint32_t fixwords = 0;              // bit per output word: recompute its 4 bytes exactly
 #pragma unroll
             for (int ow = 0; ow < G::OUT_B / 4; ow++) {
                 float xa[4], xb[4];
@@ -296,29 +297,30 @@ lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                 const uint32_t qb = quantise4(xb[0], xb[1], xb[2], xb[3]);
                 outw[ow] = qa;
                 if (p0mask) zor |= h_force;                  // inexact alignment: phase-0 samples always recomputed
-                const uint32_t d = qa ^ qb;
-                if ((d | (zor & 0x80000000u)) != 0) {        // rare
-                    uint32_t m4 = (zor & 0x80000000u) ? p0mask : 0u;
-                    m4 |= ((d & 0xffu) ? 1u : 0u) | ((d & 0xff00u) ? 2u : 0u) | ((d & 0xff0000u) ? 4u : 0u) | ((d & 0xff000000u) ? 8u : 0u);
-                    fixbytes |= (unsigned long long)m4 << (4 * ow);
-                }
+                // branch-free flag: the word is recomputed exactly if a truncation is in doubt (qa != qb)
+                // or a phase-0 sample may flip (sign of zor)
+                fixwords |= (((qa ^ qb) | (zor & 0x80000000u)) != 0 ? 1u : 0u) << ow;
             }
             uint8_t *drow = &sm.ring[slot0 + lr][g * G::OUT_B];
             uint4 *dst = reinterpret_cast<uint4 *>(drow);
 #pragma unroll
             for (int v4 = 0; v4 < G::OUT_B / 16; v4++)
                 dst[v4] = make_uint4(outw[4 * v4], outw[4 * v4 + 1], outw[4 * v4 + 2], outw[4 * v4 + 3]);
-            while (fixbytes) {                               // rare: exact recomputation of one output byte
-                const int b = __ffsll((long long)fixbytes) - 1;
-                fixbytes &= fixbytes - 1;
-                if (g * G::OUT_B + b >= valid_bytes) continue;
-                const int ob = obyte0 + g * G::OUT_B + b;                // global output byte column
-                const int xx = ob / C, c = ob - xx * C;
-                const int first = (xx * D) / N - A + 1;                    // first tap pixel (full_TB.h:59)
-                const int ph = (xx * D) % N;
-                const double *w = (p.uniform_x && N <= 8) ? &p.wdtab[ph * 8] : p.wdx + (long long)xx * TAPS;
-                drow[b] = exact_taps<TAPS>(srow + G::PAD_L + first * C + c - ibyte0, C, w);
-                n_strict++;
+            while (fixwords) {                               // rare: exact recomputation of one output word
+                const int ow = __ffs(fixwords) - 1;
+                fixwords &= fixwords - 1;
+#pragma unroll 1
+                for (int e = 0; e < 4; e++) {
+                    const int b = 4 * ow + e;
+                    if (g * G::OUT_B + b >= valid_bytes) break;
+                    const int ob = obyte0 + g * G::OUT_B + b;            // global output byte column
+                    const int xx = ob / C, c = ob - xx * C;
+                    const int first = (xx * D) / N - A + 1;                // first tap pixel (full_TB.h:59)
+                    const int ph = (xx * D) % N;
+                    const double *w = (p.uniform_x && N <= 8) ? &p.wdtab[ph * 8] : p.wdx + (long long)xx * TAPS;
+                    drow[b] = exact_taps<TAPS>(srow + G::PAD_L + first * C + c - ibyte0, C, w);
+                    n_strict++;
+                }
             }
         }
         __syncthreads();
@@ -337,7 +339,7 @@ lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                 const int t0 = (rb - A - G::S0) / D;               // exact division (also for negative values)
                 const int ybase = N * t0;
                 uint8_t *obase = ocol + (long long)(ybase - p.out_row0) * opitch;
-                unsigned long long fixmask = 0;                    // 4 bits per output row: bytes to recompute exactly
+                uint32_t fixrows = 0;                              // bit per output row: recompute this thread's word exactly
                 const bool interior = (ybase >= ys) && (ybase + G::YSPAN <= ye);
                 auto body = [&](auto check_tag) {
                     constexpr bool CHECK = decltype(check_tag)::value;
@@ -368,7 +370,7 @@ lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                                     }
                                 const uint32_t zor = v_force | __float_as_uint(z0.x) | __float_as_uint(z0.y) |
                                                      __float_as_uint(z1.x) | __float_as_uint(z1.y);
-                                if (zor & v_signmask) fixmask |= 15ull << (4 * yy);
+                                fixrows |= ((zor & v_signmask) != 0 ? 1u : 0u) << yy;
                             } else {
                                 float2 a0 = make_float2(-guard, -guard), a1 = a0;
 #pragma unroll
@@ -380,34 +382,35 @@ lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                                 const float2 gg = make_float2(g2, g2);
                                 const float2 b0 = __fadd2_rn(a0, gg), b1 = __fadd2_rn(a1, gg);
                                 q = quantise4(a0.x, a0.y, a1.x, a1.y);
-                                const uint32_t d = q ^ quantise4(b0.x, b0.y, b1.x, b1.y);
-                                if (d != 0) {                   // rare
-                                    const uint32_t m4 = ((d & 0xffu) ? 1u : 0u) | ((d & 0xff00u) ? 2u : 0u) |
-                                                        ((d & 0xff0000u) ? 4u : 0u) | ((d & 0xff000000u) ? 8u : 0u);
-                                    fixmask |= (unsigned long long)m4 << (4 * yy);
-                                }
+                                fixrows |= (q != quantise4(b0.x, b0.y, b1.x, b1.y) ? 1u : 0u) << yy;
                             }
                             *reinterpret_cast<uint32_t *>(obase + (long long)yy * opitch) = q;
                         }
                     }
                 };
                 if (interior) body(std::false_type{}); else body(std::true_type{});
-                while (fixmask) {                                   // rare: exact recomputation of one output byte
-                    const int bit = __ffsll((long long)fixmask) - 1;
-                    fixmask &= fixmask - 1;
-                    const int yy = bit >> 2, e = bit & 3;
+                while (fixrows) {                                   // rare: exact recomputation of one output word
+                    const int yy = __ffs(fixrows) - 1;
+                    fixrows &= fixrows - 1;
                     const int y = ybase + yy;
                     const int first = (y * D) / N - A + 1;          // first tap row (full_TB.h:72)
                     const int ph = (y * D) % N;
                     const double *w = (p.uniform_y && N <= 8) ? &p.wdtab[ph * 8] : p.wdy + (long long)y * TAPS;
-                    double sum = 0.0;                               // full_TB.h:71-75 on the uint8 intermediate rows
+                    const uint8_t *t0p = vcol + ((first - rs) % G::RING) * SWM;
+                    uint32_t q = 0;
+#pragma unroll 1
+                    for (int e = 0; e < 4; e++) {
+                        double sum = 0.0;                           // full_TB.h:71-75 on the uint8 intermediate rows
 #pragma unroll
-                    for (int k = 0; k < TAPS; k++) {
-                        const uint8_t v = vcol[((first + k - rs) % G::RING) * SWM + e];
-                        sum = __dadd_rn(sum, __dmul_rn((double)v, w[k]));
+                        for (int k = 0; k < TAPS; k++) {
+                            const int slot = (first - rs + k) % G::RING;
+                            sum = __dadd_rn(sum, __dmul_rn((double)vcol[slot * SWM + e], w[k]));
+                        }
+                        q |= (uint32_t)quantise_f64(sum) << (8 * e);
                     }
-                    obase[(long long)yy * opitch + e] = quantise_f64(sum);
-                    n_strict++;
+                    (void)t0p;
+                    *reinterpret_cast<uint32_t *>(obase + (long long)yy * opitch) = q;
+                    n_strict += 4;
                 }
             }
         }
@@ -465,7 +468,7 @@ int launch_one(const KParams &k, const FastHostTables &t, cudaStream_t s) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int min_periods = std::max(1, (4 * G::RB) / D);
-    const int ctas_per_sm = NT == 128 ? 5 : 2;
+    const int ctas_per_sm = NT == 128 ? 6 : 3;
     int segs = (int)((8LL * ctas_per_sm * sms + (long long)strips * k.n_frames - 1) / ((long long)strips * k.n_frames));
     segs = std::max(1, std::min(segs, std::max(1, vperiods / min_periods)));
     int seg_periods = (vperiods + segs - 1) / segs;
@@ -522,6 +525,8 @@ int launch_fast(const KParams &k, const FastHostTables &t, int *kernel_id, cudaS
     if (k.n_frames > 1 && (k.in_frame_stride % 16 != 0 || k.out_frame_stride % 4 != 0)) return -1;
     if (k.out_rows >= 65536) return -1;   // list entries hold the row in 16 bits per segment; keep it simple
     const int C = k.channels, A = k.a, N = k.scale_n, D = k.scale_d;
+    // tuning knob (tools only): LZB_NT=256 selects 256-thread CTAs with 1024-byte strips
+    static const int nt = [] { const char *e = getenv("LZB_NT"); return e ? atoi(e) : 128; }();
     // KM: taps whose phase-0 residue is negative (nonzero filter constant); the host table must agree
     int km = 0;
     for (int q = 0; q < 2 * A; q++)
@@ -529,6 +534,7 @@ int launch_fast(const KParams &k, const FastHostTables &t, int *kernel_id, cudaS
 #define LZ_CASE(c, a, n, d, ph, kmask, id)                                                             \
     if (C == c && A == a && N == n && D == d && (km & ~(kmask)) == 0) {                                 \
         *kernel_id = id;                                                                                \
+        if (nt == 256) return launch_one<c, a, n, d, ph, kmask, 256>(k, t, s);                          \
         return launch_one<c, a, n, d, ph, kmask, 128>(k, t, s);                                         \
     }
     // a = 3: sin(2*pi) < 0 in double, so the |d| = 2 taps (k = 0 and k = 4) carry negative residues
