@@ -26,6 +26,7 @@
 // filter of plan.cpp and recomputed exactly when it fails.  Recomputations are deferred to
 // per-CTA lists so that they run 32 lanes wide.
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <type_traits>
 #include <cuda.h>
@@ -118,6 +119,7 @@ struct FastParams {
     int uniform_x, uniform_y; // double weights identical for all coordinates of a phase -> wdtab usable
     int strict_v_identity;    // 0 with LANCZOS_FLAG_FAST_ALIGNED
     float align_k[8];         // phase-0 "cannot flip" constants
+    int align_ki[8];          // the same, ceil(K * 2^16), for the integer re-check in the slow paths
     float wtab[32 * 8];       // polyphase table [N][8] (padded to 8 taps), N <= 32
     double wdtab[8 * 8];      // double polyphase table [N][8] for N <= 8 (valid when uniform_*)
     unsigned long long *strict_counter;
@@ -169,11 +171,20 @@ __host__ __device__ constexpr int cdiv_c(int a, int b) { return (a + b - 1) / b;
 // Exact restatement of full_TB.h:58-63 for one sample whose 2a taps are `stride` bytes apart in
 // shared memory (taps outside the image were zero-filled by TMA: 0*w adds +-0, same bits).
 template <int TAPS>
-__device__ __noinline__ uint8_t exact_taps(const uint8_t *tap0, int stride, const double *w) {
+__device__ __forceinline__ uint8_t exact_taps(const uint8_t *tap0, int stride, const double *w) {
     double sum = 0.0;
 #pragma unroll
     for (int k = 0; k < TAPS; k++) sum = __dadd_rn(sum, __dmul_rn((double)tap0[k * stride], w[k]));
     return quantise_f64(sum);
+}
+// Integer form of the phase-0 "cannot flip" filter (plan.cpp): true = the reference provably returns v.
+template <int TAPS, int KM>
+__device__ __forceinline__ bool phase0_safe(const uint8_t *tap0, int stride, const int *ki) {
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < TAPS; k++)
+        if ((KM >> k) & 1) s += ki[k] * (int)tap0[k * stride];
+    return s <= ((int)tap0[(TAPS / 2 - 1) * stride] << 16);
 }
 
 template <int C, int A, int N, int D, int PH, int KM, int NT>
@@ -263,7 +274,7 @@ lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                 word_to_f32x4(src[wi], f[4 * wi], f[4 * wi + 1], f[4 * wi + 2], f[4 * wi + 3]);
             // window byte k (k = 0 is HALO_L bytes left of the item's own input) = f[MIS + k] * 2^24
             uint32_t outw[G::OUT_B / 4];
-            uint32_t fixwords = 0;              // bit per output word: recompute its 4 bytes exactly
+            uint32_t fix_g = 0, fix_z = 0;      // bit per output word: truncation in doubt / phase-0 sample may flip
 #pragma unroll
             for (int ow = 0; ow < G::OUT_B / 4; ow++) {
                 float xa[4], xb[4];
@@ -299,16 +310,19 @@ lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                 if (p0mask) zor |= h_force;                  // inexact alignment: phase-0 samples always recomputed
                 // branch-free flag: the word is recomputed exactly if a truncation is in doubt (qa != qb)
                 // or a phase-0 sample may flip (sign of zor)
-                fixwords |= (((qa ^ qb) | (zor & 0x80000000u)) != 0 ? 1u : 0u) << ow;
+                fix_g |= (qa != qb ? 1u : 0u) << ow;
+                fix_z |= (zor >> 31) << ow;
             }
             uint8_t *drow = &sm.ring[slot0 + lr][g * G::OUT_B];
             uint4 *dst = reinterpret_cast<uint4 *>(drow);
 #pragma unroll
             for (int v4 = 0; v4 < G::OUT_B / 16; v4++)
                 dst[v4] = make_uint4(outw[4 * v4], outw[4 * v4 + 1], outw[4 * v4 + 2], outw[4 * v4 + 3]);
-            while (fixwords) {                               // rare: exact recomputation of one output word
+            uint32_t fixwords = fix_g | fix_z;
+            while (fixwords) {                               // rare: exact recomputation inside one output word
                 const int ow = __ffs(fixwords) - 1;
                 fixwords &= fixwords - 1;
+                const bool in_doubt = (fix_g >> ow) & 1u;
 #pragma unroll 1
                 for (int e = 0; e < 4; e++) {
                     const int b = 4 * ow + e;
@@ -317,8 +331,14 @@ lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                     const int xx = ob / C, c = ob - xx * C;
                     const int first = (xx * D) / N - A + 1;                // first tap pixel (full_TB.h:59)
                     const int ph = (xx * D) % N;
+                    const uint8_t *tap0 = srow + G::PAD_L + first * C + c - ibyte0;
+                    if (ph == 0) {
+                        if (p.exact_x && phase0_safe<TAPS, KM>(tap0, C, p.align_ki)) continue;
+                    } else if (!in_doubt) {
+                        continue;
+                    }
                     const double *w = (p.uniform_x && N <= 8) ? &p.wdtab[ph * 8] : p.wdx + (long long)xx * TAPS;
-                    drow[b] = exact_taps<TAPS>(srow + G::PAD_L + first * C + c - ibyte0, C, w);
+                    drow[b] = exact_taps<TAPS>(tap0, C, w);
                     n_strict++;
                 }
             }
@@ -389,28 +409,32 @@ lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                     }
                 };
                 if (interior) body(std::false_type{}); else body(std::true_type{});
-                while (fixrows) {                                   // rare: exact recomputation of one output word
+                while (fixrows) {                                   // rare: exact recomputation inside one output word
                     const int yy = __ffs(fixrows) - 1;
                     fixrows &= fixrows - 1;
                     const int y = ybase + yy;
                     const int first = (y * D) / N - A + 1;          // first tap row (full_TB.h:72)
                     const int ph = (y * D) % N;
                     const double *w = (p.uniform_y && N <= 8) ? &p.wdtab[ph * 8] : p.wdy + (long long)y * TAPS;
-                    const uint8_t *t0p = vcol + ((first - rs) % G::RING) * SWM;
-                    uint32_t q = 0;
+                    // the 2a tap rows sit in consecutive ring slots unless the ring wraps inside the window
+                    const int s0 = (first - rs) % G::RING;
+                    uint8_t *orow = obase + (long long)yy * opitch;
 #pragma unroll 1
                     for (int e = 0; e < 4; e++) {
-                        double sum = 0.0;                           // full_TB.h:71-75 on the uint8 intermediate rows
+                        uint8_t q;
+                        if (s0 + TAPS <= G::RING) {
+                            const uint8_t *tap0 = vcol + s0 * SWM + e;
+                            q = exact_taps<TAPS>(tap0, SWM, w);    // full_TB.h:71-75 on the uint8 intermediate rows
+                        } else {
+                            double sum = 0.0;
 #pragma unroll
-                        for (int k = 0; k < TAPS; k++) {
-                            const int slot = (first - rs + k) % G::RING;
-                            sum = __dadd_rn(sum, __dmul_rn((double)vcol[slot * SWM + e], w[k]));
+                            for (int k = 0; k < TAPS; k++)
+                                sum = __dadd_rn(sum, __dmul_rn((double)vcol[((s0 + k) % G::RING) * SWM + e], w[k]));
+                            q = quantise_f64(sum);
                         }
-                        q |= (uint32_t)quantise_f64(sum) << (8 * e);
+                        orow[e] = q;
+                        n_strict++;
                     }
-                    (void)t0p;
-                    *reinterpret_cast<uint32_t *>(obase + (long long)yy * opitch) = q;
-                    n_strict += 4;
                 }
             }
         }
@@ -496,6 +520,7 @@ int launch_one(const KParams &k, const FastHostTables &t, cudaStream_t s) {
     p.uniform_x = t.uniform_x; p.uniform_y = t.uniform_y;
     p.strict_v_identity = (k.flags & LANCZOS_FLAG_FAST_ALIGNED) ? 0 : 1;
     for (int i = 0; i < 8; i++) p.align_k[i] = i < 2 * A ? t.align_k[i] : 0.f;
+    for (int i = 0; i < 8; i++) p.align_ki[i] = (int)std::ceil((double)p.align_k[i] * 65536.0 * 1.0001);
     for (int ph = 0; ph < N; ph++)
         for (int q = 0; q < 8; q++) p.wtab[ph * 8 + q] = q < 2 * A ? t.phase_w[ph * 2 * A + q] * 16777216.f : 0.f;  // x 2^24, see kPixUnscale
     for (int ph = 0; ph < N && ph < 8; ph++)

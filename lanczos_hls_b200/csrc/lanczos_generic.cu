@@ -142,6 +142,13 @@ __global__ void __launch_bounds__(128) lanczos_alias_rows_kernel(const KParams p
         });
     };
 
+    // horizontal results of the input rows the recurrence touches, computed once per row
+    constexpr int kMaxT = 32;
+    uint8_t T[kMaxT];
+    const bool cached = p.alias_in_rows <= kMaxT;
+    if (cached)
+        for (int i = 0; i < p.alias_in_rows; i++) T[i] = mid(i);
+
     uint8_t fin[8];  // final values of rows (xx, xx+taps): index row & 7
     for (int k = 0; k < 8; k++) fin[k] = 0;
     for (int yy = p.alias_top_row; yy >= 0; yy--) {
@@ -151,7 +158,7 @@ __global__ void __launch_bounds__(128) lanczos_alias_rows_kernel(const KParams p
         for (int k = 0; k < taps; k++) {
             const int i = first + k;
             if (i < 0 || i >= p.in_h) continue;  // full_TB.h:72 clips the window
-            const uint8_t v = (i > yy) ? fin[i & 7] : mid(i);
+            const uint8_t v = (i > yy) ? fin[i & 7] : (cached ? T[i] : mid(i));
             sum = __dadd_rn(sum, __dmul_rn((double)v, wy[k]));
         }
         const uint8_t q = quantise_f64(sum);
