@@ -155,8 +155,9 @@ struct Geo {
     static_assert(RING >= 2 * RB + TAPS && RING % RB == 0, "ring too small for barrier-free V/H overlap");
     static_assert(BOX_B / 4 <= 256, "TMA box too wide");
     static_assert(N <= 32, "phase table too large for kernel params");
+    static constexpr int VROWS = ((S0 + UNR) * N + D - 1) / D - (S0 * N + D - 1) / D;  // output rows per V block
     static_assert(YSPAN <= 32, "fix mask (bit per output row) too small");
-    static_assert(OUT_B / 4 <= 32, "fix mask (bit per output word) too small");
+    static_assert(VROWS <= 16 && OUT_B / 4 <= 16, "fix queue (16 entries per lane) too small");
 };
 
 template <class G>
@@ -164,27 +165,67 @@ struct __align__(128) FastSmem {
     uint8_t in[2][G::STAGE_B];            // TMA destinations (double buffered), row lr at lr * BOX_B
     uint8_t ring[G::RING][G::SW_MAX];     // H-pass results (uint8), row r lives in slot (r - rs) % RING
     unsigned long long bar[2];
+    uint16_t fixq[G::THREADS / 32][32 * 16];  // per-warp queue of words to look at again (lane << 5 | index)
+    uint16_t fixb[G::THREADS / 32][32 * 4];   // per-warp queue of bytes to recompute exactly (batch lane << 5 | byte)
 };
 
 __host__ __device__ constexpr int cdiv_c(int a, int b) { return (a + b - 1) / b; }
 
 // Exact restatement of full_TB.h:58-63 for one sample whose 2a taps are `stride` bytes apart in
 // shared memory (taps outside the image were zero-filled by TMA: 0*w adds +-0, same bits).
-template <int TAPS>
-__device__ __forceinline__ uint8_t exact_taps(const uint8_t *tap0, int stride, const double *w) {
+// (double)byte is formed as (2^52 + b) - 2^52 on the FP64 pipe: I2F.F64 runs on the slow XU unit.
+template <int TAPS, class W>
+__device__ __forceinline__ uint8_t exact_taps(const uint8_t *tap0, int stride, W weight) {
     double sum = 0.0;
 #pragma unroll
-    for (int k = 0; k < TAPS; k++) sum = __dadd_rn(sum, __dmul_rn((double)tap0[k * stride], w[k]));
+    for (int k = 0; k < TAPS; k++) {
+        const double v = __hiloint2double(0x43300000, (int)tap0[k * stride]) - 4503599627370496.0;
+        sum = __dadd_rn(sum, __dmul_rn(v, weight(k)));
+    }
     return quantise_f64(sum);
 }
-// Integer form of the phase-0 "cannot flip" filter (plan.cpp): true = the reference provably returns v.
+// Sharper integer form of the phase-0 "cannot flip" filter (plan.cpp), used on the samples the
+// cheap fp32 filter flagged.  true = the reference provably returns v:
+//   half the spacing of doubles below v is h(v) = 2^ceil(log2 v) * 2^-54 (v a power of two: the
+//   spacing halves below it).  The running double sum stays >= v if the negative residues before
+//   the centre tap sum to <= h(v) and those after it are each <= h(v) (their sum is used, which is
+//   stricter).  ki[k] = ceil(|w_k| * 2^54 / 0.99 * 2^16), so "sum ki*b <= H << 16" is that test.
 template <int TAPS, int KM>
 __device__ __forceinline__ bool phase0_safe(const uint8_t *tap0, int stride, const int *ki) {
-    int s = 0;
+    constexpr int CEN = TAPS / 2 - 1;
+    const int v = tap0[CEN * stride];
+    if (v == 0) return true;                               // the quantiser clamps at 0 either way
+    const int H = (v <= 1) ? 1 : (1 << (32 - __clz(v - 1)));
+    int pre = 0, post = 0;
 #pragma unroll
     for (int k = 0; k < TAPS; k++)
-        if ((KM >> k) & 1) s += ki[k] * (int)tap0[k * stride];
-    return s <= ((int)tap0[(TAPS / 2 - 1) * stride] << 16);
+        if ((KM >> k) & 1) {
+            if (k < CEN) pre += ki[k] * (int)tap0[k * stride];
+            else post += ki[k] * (int)tap0[k * stride];
+        }
+    return pre <= (H << 16) && post <= (H << 16);
+}
+
+// Spread the set bits of every lane's `bits` over the warp: entries (lane << 5 | bit) [| 0x8000 if the bit is
+// also set in `gbits`] are written to the per-warp queue `q`; returns their number. `amask` must be a prefix
+// of the warp (lanes 0..n-1), every lane of it must call.
+__device__ __forceinline__ int warp_enqueue(uint32_t bits, uint32_t gbits, unsigned amask, int lane, uint16_t *q) {
+    const int cnt = __popc(bits);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(amask, incl, d);
+        if (lane >= d) incl += t;
+    }
+    int pos = incl - cnt;
+    const int total = __shfl_sync(amask, incl, __popc(amask) - 1);
+    while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        q[pos++] = (uint16_t)((lane << 5) | b | (((gbits >> b) & 1u) << 15));
+    }
+    __syncwarp(amask);
+    return total;
 }
 
 template <int C, int A, int N, int D, int PH, int KM, int NT>
@@ -264,7 +305,12 @@ lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
         const int slot0 = (chunk % (G::RING / G::RB)) * G::RB;   // ring slot of this chunk's first row (no wrap inside)
 
         // ------------------------------ H pass ------------------------------
-        for (int item = tid; item < G::RB * groups; item += NT) {
+        const int lane = tid & 31;
+        uint16_t *wq = sm.fixq[tid >> 5], *wb = sm.fixb[tid >> 5];
+        for (int item0 = 0; item0 < G::RB * groups; item0 += NT) {
+            const int item = item0 + tid;
+            const unsigned hmask = __ballot_sync(0xffffffffu, item < G::RB * groups);
+            if (item >= G::RB * groups) continue;
             const int lr = item / groups, g = item - lr * groups;
             const uint8_t *srow = &sm.in[st][lr * G::BOX_B];
             const uint32_t *src = reinterpret_cast<const uint32_t *>(srow + G::WIN0 + g * G::IN_B);
@@ -290,11 +336,16 @@ lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                     if (ph == 0) {
                         const float v = f[G::MIS + base + (A - 1) * C];
                         xa[e] = xb[e] = v * kPixUnscale;
-                        float z = v;                        // "cannot flip" filter of plan.cpp: z >= 0 -> output is v
+                        // "cannot flip" filter of plan.cpp, one test per side of the centre tap:
+                        // v - sum K_k*b_k >= 0 over the negative residues before / after it -> output is v
+                        float zpre = v, zpost = v;
 #pragma unroll
                         for (int k = 0; k < TAPS; k++)
-                            if ((KM >> k) & 1) z = fmaf(f[G::MIS + base + k * C], -p.align_k[k], z);
-                        zor |= __float_as_uint(z);
+                            if ((KM >> k) & 1) {
+                                if (k < A - 1) zpre = fmaf(f[G::MIS + base + k * C], -p.align_k[k], zpre);
+                                else zpost = fmaf(f[G::MIS + base + k * C], -p.align_k[k], zpost);
+                            }
+                        zor |= __float_as_uint(zpre) | __float_as_uint(zpost);
                         p0mask |= 1u << e;
                     } else {
                         float acc = -guard;
@@ -318,28 +369,50 @@ lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
 #pragma unroll
             for (int v4 = 0; v4 < G::OUT_B / 16; v4++)
                 dst[v4] = make_uint4(outw[4 * v4], outw[4 * v4 + 1], outw[4 * v4 + 2], outw[4 * v4 + 3]);
-            uint32_t fixwords = fix_g | fix_z;
-            while (fixwords) {                               // rare: exact recomputation inside one output word
-                const int ow = __ffs(fixwords) - 1;
-                fixwords &= fixwords - 1;
-                const bool in_doubt = (fix_g >> ow) & 1u;
-#pragma unroll 1
-                for (int e = 0; e < 4; e++) {
+            // rare: words whose truncation is in doubt or whose phase-0 samples may flip.  The warp pools
+            // them (uniform noise flags ~1/4 of the words): stage A re-checks every byte of a flagged word
+            // with the integer phase-0 filter, stage B pools the surviving bytes, stage C recomputes them
+            // exactly, one byte per lane.
+            if (__ballot_sync(hmask, (fix_g | fix_z) != 0)) {
+                const int nfix = warp_enqueue(fix_g | fix_z, fix_g, hmask, lane, wq);
+                const int nact = __popc(hmask);
+                auto decode = [&](uint32_t ent, int e, const uint8_t *&tap0, uint8_t *&dst, int &ph, int &xx) -> bool {
+                    const int item_l = item - lane + (int)((ent >> 5) & 31u), ow = (int)(ent & 31u);
+                    const int lr_l = item_l / groups, g_l = item_l - lr_l * groups;
                     const int b = 4 * ow + e;
-                    if (g * G::OUT_B + b >= valid_bytes) break;
-                    const int ob = obyte0 + g * G::OUT_B + b;            // global output byte column
-                    const int xx = ob / C, c = ob - xx * C;
-                    const int first = (xx * D) / N - A + 1;                // first tap pixel (full_TB.h:59)
-                    const int ph = (xx * D) % N;
-                    const uint8_t *tap0 = srow + G::PAD_L + first * C + c - ibyte0;
-                    if (ph == 0) {
-                        if (p.exact_x && phase0_safe<TAPS, KM>(tap0, C, p.align_ki)) continue;
-                    } else if (!in_doubt) {
-                        continue;
+                    if (g_l * G::OUT_B + b >= valid_bytes) return false;
+                    const int ob = obyte0 + g_l * G::OUT_B + b;              // global output byte column
+                    xx = ob / C;
+                    const int c = ob - xx * C;
+                    const int first = (xx * D) / N - A + 1;                    // first tap pixel (full_TB.h:59)
+                    ph = (xx * D) % N;
+                    tap0 = &sm.in[st][lr_l * G::BOX_B] + G::PAD_L + first * C + c - ibyte0;
+                    dst = &sm.ring[slot0 + lr_l][g_l * G::OUT_B + b];
+                    return true;
+                };
+                for (int base = 0; base < nfix; base += nact) {
+                    uint32_t m4 = 0;
+                    if (base + lane < nfix) {
+                        const uint32_t ent = wq[base + lane];
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const uint8_t *tap0; uint8_t *dst; int ph, xx;
+                            if (!decode(ent, e, tap0, dst, ph, xx)) continue;
+                            const bool need = (ph == 0) ? !(p.exact_x && phase0_safe<TAPS, KM>(tap0, C, p.align_ki))
+                                                        : (ent >> 15) != 0;
+                            m4 |= (need ? 1u : 0u) << e;
+                        }
                     }
-                    const double *w = (p.uniform_x && N <= 8) ? &p.wdtab[ph * 8] : p.wdx + (long long)xx * TAPS;
-                    drow[b] = exact_taps<TAPS>(tap0, C, w);
-                    n_strict++;
+                    const int nb = warp_enqueue(m4, 0u, hmask, lane, wb);
+                    for (int j = lane; j < nb; j += nact) {
+                        const uint32_t eb = wb[j];
+                        const uint8_t *tap0; uint8_t *dst; int ph, xx;
+                        decode(wq[base + (int)(eb >> 5)], (int)(eb & 31u), tap0, dst, ph, xx);
+                        if (p.uniform_x && N <= 8) *dst = exact_taps<TAPS>(tap0, C, [&](int k) { return p.wdtab[ph * 8 + k]; });
+                        else *dst = exact_taps<TAPS>(tap0, C, [&](int k) { return p.wdx[(long long)xx * TAPS + k]; });
+                        n_strict++;
+                    }
+                    __syncwarp(hmask);
                 }
             }
         }
@@ -348,6 +421,7 @@ lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
         if (tid == 0 && chunk + 2 < nchunks) issue(chunk + 2);
 
         // ------------------------------ V pass ------------------------------
+        const unsigned vmask = __ballot_sync(0xffffffffu, v_active);
         if (v_active) {
             const int r0 = rs + chunk * G::RB;                    // first row of this chunk
 #pragma unroll 1
@@ -409,31 +483,48 @@ lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                     }
                 };
                 if (interior) body(std::false_type{}); else body(std::true_type{});
-                while (fixrows) {                                   // rare: exact recomputation inside one output word
-                    const int yy = __ffs(fixrows) - 1;
-                    fixrows &= fixrows - 1;
-                    const int y = ybase + yy;
-                    const int first = (y * D) / N - A + 1;          // first tap row (full_TB.h:72)
-                    const int ph = (y * D) % N;
-                    const double *w = (p.uniform_y && N <= 8) ? &p.wdtab[ph * 8] : p.wdy + (long long)y * TAPS;
-                    // the 2a tap rows sit in consecutive ring slots unless the ring wraps inside the window
-                    const int s0 = (first - rs) % G::RING;
-                    uint8_t *orow = obase + (long long)yy * opitch;
-#pragma unroll 1
-                    for (int e = 0; e < 4; e++) {
-                        uint8_t q;
-                        if (s0 + TAPS <= G::RING) {
-                            const uint8_t *tap0 = vcol + s0 * SWM + e;
-                            q = exact_taps<TAPS>(tap0, SWM, w);    // full_TB.h:71-75 on the uint8 intermediate rows
-                        } else {
-                            double sum = 0.0;
+                // rare: rows whose truncation is in doubt / whose phase-0 word may flip, pooled over the warp
+                // (same three stages as in the H pass)
+                if (__ballot_sync(vmask, fixrows != 0)) {
+                    const int nfix = warp_enqueue(fixrows, 0u, vmask, lane, wq);
+                    const int nact = __popc(vmask);
+                    auto decode = [&](uint32_t ent, int &y, int &ph, int &s0, const uint8_t *&col, uint8_t *&orow) {
+                        const int dl = (int)((ent >> 5) & 31u) - lane, yy = (int)(ent & 31u);   // owner lane offset, row
+                        y = ybase + yy;
+                        ph = (y * D) % N;
+                        s0 = ((y * D) / N - A + 1 - rs) % G::RING;       // ring slot of the first tap row (full_TB.h:72)
+                        col = vcol + 4 * dl;
+                        orow = obase + (long long)yy * opitch + 4 * dl;
+                    };
+                    for (int base = 0; base < nfix; base += nact) {
+                        uint32_t m4 = 0;
+                        if (base + lane < nfix) {
+                            int y, ph, s0; const uint8_t *col; uint8_t *orow;
+                            decode(wq[base + lane], y, ph, s0, col, orow);
+                            m4 = 15u;
+                            if (ph == 0 && p.exact_y && s0 + TAPS <= G::RING) {
+                                m4 = 0;
 #pragma unroll
-                            for (int k = 0; k < TAPS; k++)
-                                sum = __dadd_rn(sum, __dmul_rn((double)vcol[((s0 + k) % G::RING) * SWM + e], w[k]));
-                            q = quantise_f64(sum);
+                                for (int e = 0; e < 4; e++)
+                                    m4 |= (phase0_safe<TAPS, KM>(col + s0 * SWM + e, SWM, p.align_ki) ? 0u : 1u) << e;
+                            }
                         }
-                        orow[e] = q;
-                        n_strict++;
+                        const int nb = warp_enqueue(m4, 0u, vmask, lane, wb);
+                        for (int j = lane; j < nb; j += nact) {
+                            const uint32_t eb = wb[j];
+                            const int e = (int)(eb & 31u);
+                            int y, ph, s0; const uint8_t *col; uint8_t *orow;
+                            decode(wq[base + (int)(eb >> 5)], y, ph, s0, col, orow);
+                            // full_TB.h:71-75 on the uint8 intermediate rows; the 2a tap rows sit in consecutive
+                            // ring slots unless the ring wraps inside the window
+                            uint8_t taps_b[TAPS];
+#pragma unroll
+                            for (int k = 0; k < TAPS; k++) taps_b[k] = col[((s0 + k) % G::RING) * SWM + e];
+                            if (p.uniform_y && N <= 8) orow[e] = exact_taps<TAPS>(taps_b, 1, [&](int k) { return p.wdtab[ph * 8 + k]; });
+                            else orow[e] = exact_taps<TAPS>(taps_b, 1, [&](int k) { return p.wdy[(long long)y * TAPS + k]; });
+                            n_strict++;
+                        }
+                        __syncwarp(vmask);
                     }
                 }
             }
