@@ -27,9 +27,14 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-IN_W, IN_H, OUT_W, OUT_H, CH, A, SN, SD = 1920, 1080, 3840, 2160, 3, 3, 2, 1
-WORKLOAD = "1920x1080->3840x2160 RGB8 2x Lanczos-3 (BASELINE configs[1])"
-ALGO_BYTES_PER_FRAME = IN_W * IN_H * CH + OUT_W * OUT_H * CH      # 31,104,000
+# name -> (in_w, in_h, out_w, out_h, channels, a, N, D, default frames per GPU per step, label)
+WORKLOADS = {
+    "c2": (1920, 1080, 3840, 2160, 3, 3, 2, 1, 32, "1920x1080->3840x2160 RGB8 2x Lanczos-3 (BASELINE configs[1])"),
+    "c3": (2560, 1440, 3840, 2160, 4, 3, 3, 2, 32, "2560x1440->3840x2160 RGBA8 3/2 Lanczos-3 (BASELINE configs[2], frames sharded over GPUs)"),
+    "c4": (3840, 2160, 7680, 4320, 3, 3, 2, 1, 16, "3840x2160->7680x4320 RGB8 2x Lanczos-3 (BASELINE configs[3], frames sharded over GPUs)"),
+}
+IN_W, IN_H, OUT_W, OUT_H, CH, A, SN, SD, DEF_FRAMES, WORKLOAD = WORKLOADS["c2"]
+ALGO_BYTES_PER_FRAME = IN_W * IN_H * CH + OUT_W * OUT_H * CH      # 31,104,000 for c2
 OUT_PX_PER_FRAME = OUT_W * OUT_H
 # CPU sample of the same workload: a 1920x135 band -> 3840x270 (1/8 frame), reference compiled for it
 CPU_SAMPLE_CFG = (1920, 135, 3840, 270, 2, 1, 3, 3)
@@ -154,7 +159,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=32, help="frames per GPU per step")
+    ap.add_argument("--frames", type=int, default=0, help="frames per GPU per step (0 = workload default)")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 = headline (BASELINE configs[1])")
     ap.add_argument("--content", default="smooth", choices=["noise", "smooth"],
                     help="smooth = SURVEY 8d(ii) image-like content (default); noise = 8d(i) uniform noise, the worst "
                          "case for the exact re-evaluation path (reported as worst_case in the JSON line)")
@@ -163,6 +169,12 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--flags", type=int, default=0)
     args = ap.parse_args()
+    global IN_W, IN_H, OUT_W, OUT_H, CH, A, SN, SD, DEF_FRAMES, WORKLOAD, ALGO_BYTES_PER_FRAME, OUT_PX_PER_FRAME
+    IN_W, IN_H, OUT_W, OUT_H, CH, A, SN, SD, DEF_FRAMES, WORKLOAD = WORKLOADS[args.workload]
+    ALGO_BYTES_PER_FRAME = IN_W * IN_H * CH + OUT_W * OUT_H * CH
+    OUT_PX_PER_FRAME = OUT_W * OUT_H
+    if args.frames <= 0:
+        args.frames = DEF_FRAMES
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -291,7 +303,7 @@ def main():
     # ---- end to end through the host-buffer C-ABI call (pinned host memory) ----
     e2e = None
     if not args.no_e2e:
-        Fe = args.e2e_frames
+        Fe = min(args.e2e_frames, F)
         hin = lz.PinnedBuffer(Fe * IN_H * IN_W * CH)
         hout = lz.PinnedBuffer(Fe * OUT_H * OUT_W * CH)
         hin.array[:] = d_in[:Fe].reshape(-1).cpu().numpy() if Fe <= F else np.resize(d_in.reshape(-1).cpu().numpy(), hin.nbytes)
@@ -323,11 +335,11 @@ def main():
     peak, peak_src = measured_hbm_peak()
     achieved = F * ALGO_BYTES_PER_FRAME / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic_per_launch(F), "peak_source": peak_src,
+                "traffic": ncu_traffic_per_launch(F) if args.workload == "c2" else None, "peak_source": peak_src,
                 "kernel": "main fused H->V kernel, one launch per step", "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": F * ALGO_BYTES_PER_FRAME}
     cpu = None
-    if n_gpus == 1 and not args.no_cpu_baseline:
+    if n_gpus == 1 and not args.no_cpu_baseline and args.workload == "c2":
         r = run_reference_cpu(2, 0)
         cpu = {"value": r["value"], "unit": "Mpix/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
     line = {

@@ -229,3 +229,40 @@ def test_determinism_and_strict_counter(torch_cuda, lz, oracle):
     assert np.array_equal(a, b)
     assert st["kernel_launches"] >= 1 and st["alias_rows"] == 5
     assert st["strict_samples"] > 0      # noise always has sums near an integer
+
+
+def test_fast_aligned_flag_is_within_one_lsb(torch_cuda, lz, oracle):
+    """LANCZOS_FLAG_FAST_ALIGNED skips the exact re-evaluation of phase-0 ROWS: <= 1 LSB, and every
+    mismatch sits on a phase-0 row where the reference returned v-1 (sin(k*pi) residues)."""
+    for maker, seed in ((dark_hwc, 3), (noise_hwc, 4)):
+        img = maker(oracle, 270, 480, 3, seed=seed)
+        want = oracle.upscale(img, 960, 540, 3, 2, 1)
+        got = gpu_upscale(torch_cuda, lz, img, 960, 540, 3, 2, 1, flags=lz.FLAG_FAST_ALIGNED)
+        d = got.astype(np.int16) - want.astype(np.int16)
+        assert np.abs(d).max() <= 1
+        ys = np.nonzero(d)[0]
+        assert (ys % 2 == 0).all()            # 2x: phase-0 rows are the even output rows
+        assert (d[d != 0] == 1).all()         # we return v, the reference v-1
+        exact = float((d == 0).mean())
+        assert exact > 0.98, exact            # exact-match fraction stays above 98 % even on noise
+
+
+def test_generic_and_specialised_kernels_agree(torch_cuda, lz, oracle):
+    """Both code paths must give the reference's bits (kernel_id tells which one ran)."""
+    img = noise_hwc(oracle, 200, 320, 3, seed=12)
+    want = oracle.upscale(img, 640, 400, 3, 2, 1)
+    a = gpu_upscale(torch_cuda, lz, img, 640, 400, 3, 2, 1)
+    ka = lz.stats()["kernel_id"]
+    b = gpu_upscale(torch_cuda, lz, img, 640, 400, 3, 2, 1, flags=lz.FLAG_GENERIC_KERNEL)
+    kb = lz.stats()["kernel_id"]
+    assert ka == 1 and kb == 0
+    assert np.array_equal(a, want) and np.array_equal(b, want)
+
+
+def test_config4_shape_4k_to_8k_one_frame(torch_cuda, lz, oracle):
+    """BASELINE config 4 (one frame of the batch): 3840x2160 -> 7680x4320 RGB8, 2x."""
+    img = smooth_hwc(oracle, 2160, 3840, 3, seed=5)
+    img[:300, :400] = noise_hwc(oracle, 300, 400, 3, seed=6)      # a noisy corner keeps the exact path busy
+    want = oracle.upscale(img, 7680, 4320, 3, 2, 1)
+    got = gpu_upscale(torch_cuda, lz, img, 7680, 4320, 3, 2, 1)
+    assert np.array_equal(got, want)
