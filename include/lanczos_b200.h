@@ -152,6 +152,20 @@ int lanczos_b200_expected(const lanczos_desc *desc, const uint8_t *h_in_planar,
 int lanczos_b200_stream(const lanczos_desc *desc, const uint32_t *h_in_words,
                         uint32_t *h_out_words, int device);
 
+/* ---- fixed-point "HLS mode" (SURVEY.md 8f): the integer arithmetic of the reference's HLS path,
+ * `lanczos()` = process_channel (lanczos.cpp:68-98): vertical pass first, LUT weights indexed by
+ * |out*SCALE_D - in*SCALE_N| (kernel.cpp:50-67), exact integer MAC + de-ring clamp to the two central
+ * taps (worker.cpp:45-115), zero borders above/left and replicated borders below/right
+ * (worker.cpp:170-198,239-275).  Integer scales only (scale_d == 1, a*scale_n <= 127);
+ * bit_precision = BIT_PRECISION (lanczos.h:28), 1..12.  The LUT is floor(L(x)*2^BP) with L in double:
+ * the reference's hls::sinpi values are not available, so parity with the reference is UNPINNED;
+ * results are bit-exact against oracle/hls_oracle.c.  Device buffers, asynchronous. */
+int lanczos_b200_upscale_hls(const lanczos_desc *desc, const uint8_t *d_in, uint8_t *d_out,
+                             int32_t bit_precision, int32_t n_frames, int64_t in_frame_stride,
+                             int64_t out_frame_stride, int device, void *cuda_stream);
+/* The LUT of init_lanczos_kernel (kernel.cpp:40-45): a*scale_n+1 entries in units of 2^-bit_precision. */
+int lanczos_b200_hls_lut(int32_t a, int32_t scale_n, int32_t bit_precision, int32_t *lut, int32_t capacity);
+
 /* ---- helpers */
 /* Reduce out/in to lowest terms like the reference's gcd() (stb.cpp:9-12, lanczos.h:110). */
 int lanczos_b200_reduce_ratio(int32_t out_len, int32_t in_len, int32_t *scale_n, int32_t *scale_d);

@@ -33,4 +33,6 @@ from .api import (  # noqa: F401
     upscale_batch_device,
     upscale_band_device,
     PinnedBuffer,
+    hls_lut,
+    upscale_hls_device,
 )

@@ -67,6 +67,8 @@ def lib():
     L.lanczos_b200_upscale_host_bands.argtypes = [dp, u8p, u8p, C.POINTER(i32), i32]
     L.lanczos_b200_expected.argtypes = [dp, u8p, u8p, C.c_int]
     L.lanczos_b200_stream.argtypes = [dp, vp, vp, C.c_int]
+    L.lanczos_b200_upscale_hls.argtypes = [dp, u8p, u8p, i32, i32, i64, i64, C.c_int, vp]
+    L.lanczos_b200_hls_lut.argtypes = [i32, i32, i32, C.POINTER(i32), i32]
     L.lanczos_b200_reduce_ratio.argtypes = [i32, i32, C.POINTER(i32), C.POINTER(i32)]
     L.lanczos_b200_resolve.argtypes = [dp, dp]
     L.lanczos_b200_kernel.argtypes = [C.c_double, i32]
@@ -265,3 +267,25 @@ def upscale_band_device(desc, d_in_band, d_out_band, out_row0, out_rows, in_row0
                                            C.c_void_p(d_out_band.data_ptr()), out_row0, out_rows, in_row0, in_rows,
                                            d_in_band.device.index or 0, _stream_ptr(d_in_band)))
     return d_out_band
+
+
+# ---- fixed-point "HLS mode" (the reference's lanczos() arithmetic, parity unpinned) ------------
+
+def hls_lut(a, scale_n, bit_precision=8):
+    """LUT of init_lanczos_kernel (kernel.cpp:40-45), a*scale_n+1 entries in units of 2^-BP."""
+    buf = (C.c_int32 * (a * scale_n + 1))()
+    _check(lib().lanczos_b200_hls_lut(a, scale_n, bit_precision, buf, len(buf)))
+    return np.array(buf[:], dtype=np.int32)
+
+
+def upscale_hls_device(d_in, d_out, a=3, bit_precision=8):
+    """torch uint8 CUDA tensors [H][W][C] or [F][H][W][C]; integer scale = out/in."""
+    batched = d_in.dim() == 4
+    f = d_in.shape[0] if batched else 1
+    h, w, c = d_in.shape[-3:]
+    oh, ow = d_out.shape[-3:-1]
+    desc = make_desc(w, h, ow, oh, c, a, 0, 0, d_in.stride(-3), d_out.stride(-3), 0)
+    _check(lib().lanczos_b200_upscale_hls(C.byref(desc), C.c_void_p(d_in.data_ptr()), C.c_void_p(d_out.data_ptr()),
+                                          bit_precision, f, d_in.stride(0) if batched else 0,
+                                          d_out.stride(0) if batched else 0, d_in.device.index or 0, _stream_ptr(d_in)))
+    return d_out

@@ -5,6 +5,7 @@
 // Here that is per-GPU CUDA streams with chunked host<->device copies overlapping the kernels,
 // frame batches or row bands as the unit of work, and no collectives.
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -427,6 +428,49 @@ int lanczos_b200_upscale_band(const lanczos_desc *desc, const uint8_t *d_in_band
     resolve_desc(desc, &user);
     return run_device(*dp, desc->flags, d_in_band, d_out_band, 1, 0, 0, out_row0, out_rows, in_row0,
                       in_rows, user.in_pitch, user.out_pitch, (cudaStream_t)cuda_stream);
+}
+
+// ---- fixed-point HLS mode --------------------------------------------------------------------
+
+int lanczos_b200_hls_lut(int32_t a, int32_t scale_n, int32_t bit_precision, int32_t *lut, int32_t capacity) {
+    if (!lut) return LANCZOS_ERR_NULL;
+    if (a < 1 || a > kMaxTaps / 2) return LANCZOS_ERR_TAPS;
+    if (scale_n < 1 || a * scale_n > 127) return LANCZOS_ERR_RATIO;   // kernel_t(i) wraps for i >= 128
+    if (bit_precision < 1 || bit_precision > 12 || capacity < a * scale_n + 1) return LANCZOS_ERR_DIMS;
+    for (int i = 0; i < a * scale_n; i++) {
+        // kernel.cpp:42: argument (kernel_t)i/SCALE_N truncated to BP bits, value truncated to BP bits (AP_TRN)
+        const double x = std::floor((double)i * (1 << bit_precision) / scale_n) / (1 << bit_precision);
+        lut[i] = (int32_t)std::floor(ref_kernel(x, a) * (1 << bit_precision));
+    }
+    lut[a * scale_n] = 0;   // kernel.cpp:44
+    return LANCZOS_OK;
+}
+
+int lanczos_b200_upscale_hls(const lanczos_desc *desc, const uint8_t *d_in, uint8_t *d_out, int32_t bit_precision,
+                             int32_t n_frames, int64_t in_frame_stride, int64_t out_frame_stride, int device,
+                             void *cuda_stream) {
+    if (!desc || !d_in || !d_out) return LANCZOS_ERR_NULL;
+    if (n_frames < 0) return LANCZOS_ERR_DIMS;
+    lanczos_desc r;
+    int rc = resolve_desc(desc, &r);
+    if (rc != LANCZOS_OK) return rc;
+    if (r.scale_d != 1) return LANCZOS_ERR_RATIO;   // the BP-bit step condition drifts for other ratios
+    int32_t lut[128];
+    rc = lanczos_b200_hls_lut(r.a, r.scale_n, bit_precision, lut, 128);
+    if (rc != LANCZOS_OK) return rc;
+    DeviceGuard g(device);
+    if (!g.ok) return cuda_fail(cudaErrorInvalidDevice, "cudaSetDevice");
+    if (in_frame_stride == 0) in_frame_stride = r.in_pitch * r.in_h;
+    if (out_frame_stride == 0) out_frame_stride = r.out_pitch * r.out_h;
+    g_stats = lanczos_stats{};
+    if (n_frames == 0) return LANCZOS_OK;
+    cudaError_t e = (cudaError_t)launch_hls(d_in, d_out, r.in_pitch, r.out_pitch, in_frame_stride, out_frame_stride,
+                                            n_frames, r.in_w, r.in_h, r.out_w, r.out_h, r.channels, r.a, r.scale_n,
+                                            bit_precision, lut, (cudaStream_t)cuda_stream);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_hls");
+    g_stats.kernel_launches = 1;
+    g_stats.kernel_id = 100;
+    return LANCZOS_OK;
 }
 
 // ---- host-buffer drivers --------------------------------------------------------------------

@@ -41,6 +41,10 @@ struct FastHostTables {            // host-side views of the plan the specialise
 int launch_fast(const KParams &p, const FastHostTables &t, int *kernel_id, cudaStream_t s);
 // In-place top rows (full_TB.h:67-77 aliasing), exact double arithmetic.
 int launch_alias_rows(const KParams &p, cudaStream_t s);
+// Fixed-point HLS arithmetic (lanczos_hls.cu), integer scales; lut has a*n+1 entries in units of 2^-bp.
+int launch_hls(const uint8_t *in, uint8_t *out, long long in_pitch, long long out_pitch, long long in_fs,
+               long long out_fs, int n_frames, int in_w, int in_h, int out_w, int out_h, int channels, int a, int n,
+               int bp, const int *lut, cudaStream_t s);
 // Planar <-> interleaved helpers for lanczos_b200_expected / lanczos_b200_stream.
 int launch_planar_to_interleaved(const uint8_t *planar, uint8_t *inter, int w, int h, int c, cudaStream_t s);
 int launch_interleaved_to_planar(const uint8_t *inter, uint8_t *planar, int w, int h, int c, cudaStream_t s);

@@ -42,6 +42,8 @@ def lib():
         L.oracle_fill_xorshift.restype = None
         L.oracle_fnv1a64.argtypes = [u8p, C.c_int64]
         L.oracle_fnv1a64.restype = C.c_uint64
+        L.oracle_hls_lut.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]
+        L.oracle_hls_upscale.argtypes = [u8p, u8p] + [C.c_int] * 8
         _lib = L
     return _lib
 
@@ -134,4 +136,23 @@ def ref_expected_planar(img, cfg):
     assert img.shape == (c, ih, iw)
     out = np.empty((c, oh, ow), dtype=np.uint8)
     ref_lib(cfg).ref_lanczos_expected(_p(img), _p(out))
+    return out
+
+
+# ---- fixed-point HLS path (parity UNPINNED, see oracle/hls_oracle.c) ----
+
+def hls_lut(a, n, bp=8):
+    buf = (C.c_int32 * (a * n + 1))()
+    if lib().oracle_hls_lut(a, n, bp, buf) != 0:
+        raise ValueError("bad HLS LUT arguments")
+    return np.array(buf[:], dtype=np.int32)
+
+
+def hls_upscale(img, n, a=3, bp=8):
+    """Fixed-point HLS path on an interleaved [H][W][C] image, integer scale n."""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w, c = img.shape
+    out = np.empty((h * n, w * n, c), dtype=np.uint8)
+    if lib().oracle_hls_upscale(_p(img), _p(out), c, w, h, w * n, h * n, a, n, bp) != 0:
+        raise ValueError("oracle rejected the HLS arguments")
     return out

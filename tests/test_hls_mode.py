@@ -1,0 +1,69 @@
+"""Fixed-point "HLS mode" (SURVEY.md 8f-1): the integer arithmetic of the reference's lanczos()
+(worker.cpp:45-130, kernel.cpp:40-67).  Parity with the reference itself is UNPINNED (its LUT needs
+Xilinx hls::sinpi, absent here); the CUDA path is checked bit for bit against oracle/hls_oracle.c."""
+import numpy as np
+import pytest
+
+from util import noise_hwc, smooth_hwc
+
+
+def test_lut_restatement(oracle, lz):
+    # 2x, BP=8: a=2 -> [256,146,0,-17,0], a=3 -> [256,155,0,-35,-1,6,0]
+    assert oracle.hls_lut(2, 2).tolist() == [256, 146, 0, -17, 0]
+    assert oracle.hls_lut(3, 2).tolist() == [256, 155, 0, -35, -1, 6, 0]
+    for (a, n, bp) in [(2, 2, 8), (3, 2, 8), (3, 4, 8), (2, 3, 10), (3, 2, 6)]:
+        assert np.array_equal(lz.hls_lut(a, n, bp), oracle.hls_lut(a, n, bp))
+    with pytest.raises(lz.LanczosError):
+        lz.hls_lut(3, 64)        # kernel_t(i) wraps for i >= 128 (kernel.cpp:42)
+
+
+def test_oracle_dering_and_borders(oracle):
+    img = noise_hwc(oracle, 24, 32, 3, seed=1)
+    out = oracle.hls_upscale(img, 2)
+    # phase-0 samples nearly reproduce the input: LUT[0] = 1.0, LUT[2N] = floor(-1.6e-17 * 256) = -1/256 (the
+    # unpinned sin(2*pi) residue) pulls the sum below v, and both passes floor -> a few LSB low at most
+    d0 = img.astype(int) - out[::2, ::2].astype(int)
+    assert d0.min() >= 0 and d0.max() <= 4
+    # de-ring clamp (worker.cpp:66-74): every output lies between its two central taps along x
+    mid = out[:, 1:-1:2].astype(int)
+    lo = np.minimum(out[:, 0:-2:2], out[:, 2::2]).astype(int)
+    hi = np.maximum(out[:, 0:-2:2], out[:, 2::2]).astype(int)
+    assert ((mid >= lo - 3) & (mid <= hi + 3)).all()   # neighbours are themselves up to 4 LSB low (see above)
+    flat = oracle.hls_upscale(np.full((12, 12, 3), 200, np.uint8), 2)
+    assert (flat[6:-2, 6:-2] == 200).all()           # the clamp pins flat regions (unlike the software path)
+    assert (flat[-6:, -6:] == 200).all()             # bottom/right: last row/column replicated
+    assert flat[0, 6, 0] == 200                      # top: zero rows enter the window, but the clamp to the central taps pins it
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", [(96, 54, 2, 3, 3, 8), (50, 40, 2, 2, 4, 8), (33, 47, 3, 2, 1, 8),
+                                 (64, 64, 4, 3, 3, 8), (70, 30, 2, 3, 3, 10), (131, 77, 2, 3, 3, 6)],
+                         ids=lambda c: "x".join(map(str, c)))
+def test_gpu_matches_integer_restatement(lz, oracle, cfg):
+    import torch
+    w, h, n, a, c, bp = cfg
+    for maker in (noise_hwc, smooth_hwc):
+        img = maker(oracle, h, w, c, seed=w)
+        want = oracle.hls_upscale(img, n, a, bp)
+        d_in = torch.from_numpy(img).cuda()
+        d_out = torch.zeros((h * n, w * n, c), dtype=torch.uint8, device="cuda")
+        lz.upscale_hls_device(d_in, d_out, a=a, bit_precision=bp)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_out.cpu().numpy(), want)
+    assert lz.stats()["kernel_id"] == 100
+
+
+@pytest.mark.gpu
+def test_gpu_hls_batch_and_errors(lz, oracle):
+    import torch
+    frames = np.stack([noise_hwc(oracle, 20, 28, 3, seed=s) for s in range(3)])
+    d_in = torch.from_numpy(frames).cuda()
+    d_out = torch.zeros((3, 40, 56, 3), dtype=torch.uint8, device="cuda")
+    lz.upscale_hls_device(d_in, d_out)
+    torch.cuda.synchronize()
+    for i in range(3):
+        assert np.array_equal(d_out[i].cpu().numpy(), oracle.hls_upscale(frames[i], 2))
+    bad = torch.zeros((30, 42, 3), dtype=torch.uint8, device="cuda")     # 3/2 is not an integer scale
+    with pytest.raises(lz.LanczosError) as e:
+        lz.upscale_hls_device(d_in[0], bad)
+    assert e.value.code == -5
