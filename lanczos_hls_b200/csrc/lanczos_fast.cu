@@ -34,6 +34,10 @@
 #include "../../include/lanczos_b200.h"
 #include "kernels.cuh"
 
+#ifndef LZB_ALWAYS_CHECK
+#define LZB_ALWAYS_CHECK 0
+#endif
+
 namespace lzb {
 
 namespace {
@@ -229,7 +233,7 @@ __device__ __forceinline__ int warp_enqueue(uint32_t bits, uint32_t gbits, unsig
 }
 
 template <int C, int A, int N, int D, int PH, int KM, int NT>
-__global__ void __launch_bounds__(NT, (NT == 128 ? 6 : 3))
+__global__ void __launch_bounds__(NT, (NT == 128 ? 7 : 3))
 lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ FastParams p) {
     using G = Geo<C, A, N, D, PH, NT>;
     constexpr int TAPS = G::TAPS;
@@ -482,7 +486,7 @@ lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                         }
                     }
                 };
-                if (interior) body(std::false_type{}); else body(std::true_type{});
+                if (interior && !LZB_ALWAYS_CHECK) body(std::false_type{}); else body(std::true_type{});
                 // rare: rows whose truncation is in doubt / whose phase-0 word may flip, pooled over the warp
                 // (same three stages as in the H pass)
                 if (__ballot_sync(vmask, fixrows != 0)) {
@@ -583,7 +587,7 @@ int launch_one(const KParams &k, const FastHostTables &t, cudaStream_t s) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int min_periods = std::max(1, (4 * G::RB) / D);
-    const int ctas_per_sm = NT == 128 ? 6 : 3;
+    const int ctas_per_sm = NT == 128 ? 7 : 3;
     int segs = (int)((8LL * ctas_per_sm * sms + (long long)strips * k.n_frames - 1) / ((long long)strips * k.n_frames));
     segs = std::max(1, std::min(segs, std::max(1, vperiods / min_periods)));
     int seg_periods = (vperiods + segs - 1) / segs;
