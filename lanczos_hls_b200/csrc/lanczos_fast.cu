@@ -303,19 +303,35 @@ lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
     const uint32_t v_signmask = (p.exact_y && !p.strict_v_identity) ? 0u : 0x80000000u;
     const uint32_t h_force = p.exact_x ? 0u : 0x80000000u;
 
+    // H-pass work distribution is the same for every chunk: item = round * NT + tid -> (row, group)
+    constexpr int HROUNDS = (G::RB * G::MAX_GROUPS + NT - 1) / NT;
+    int h_lr[HROUNDS], h_g[HROUNDS];
+#pragma unroll
+    for (int r = 0; r < HROUNDS; r++) {
+        const int item = r * NT + tid;
+        h_lr[r] = item / groups;
+        h_g[r] = item - h_lr[r] * groups;
+    }
+    const int lane = tid & 31;
+    uint16_t *wq = sm.fixq[tid >> 5], *wb = sm.fixb[tid >> 5];
+    // running output pointer of the V pass: row (ybase - out_row0) of this thread's column, advanced per block
+    const int t0_first = (rs - A - G::S0) / D;                 // exact division (also for negative values)
+    uint8_t *obase = ocol + (long long)(N * t0_first - p.out_row0) * opitch;
+    const long long oblock = (long long)(N * (G::UNR / D)) * opitch;   // output rows per V block
+    int ybase = N * t0_first;
+
     for (int chunk = 0; chunk < nchunks; chunk++) {
         const int st = chunk & 1;
         mbar_wait(st ? bar1 : bar0, (chunk >> 1) & 1);
         const int slot0 = (chunk % (G::RING / G::RB)) * G::RB;   // ring slot of this chunk's first row (no wrap inside)
 
         // ------------------------------ H pass ------------------------------
-        const int lane = tid & 31;
-        uint16_t *wq = sm.fixq[tid >> 5], *wb = sm.fixb[tid >> 5];
-        for (int item0 = 0; item0 < G::RB * groups; item0 += NT) {
-            const int item = item0 + tid;
+#pragma unroll
+        for (int hr = 0; hr < HROUNDS; hr++) {
+            const int item = hr * NT + tid;
             const unsigned hmask = __ballot_sync(0xffffffffu, item < G::RB * groups);
             if (item >= G::RB * groups) continue;
-            const int lr = item / groups, g = item - lr * groups;
+            const int lr = h_lr[hr], g = h_g[hr];
             const uint8_t *srow = &sm.in[st][lr * G::BOX_B];
             const uint32_t *src = reinterpret_cast<const uint32_t *>(srow + G::WIN0 + g * G::IN_B);
             float f[G::NWORDS * 4];
@@ -427,16 +443,12 @@ lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
         // ------------------------------ V pass ------------------------------
         const unsigned vmask = __ballot_sync(0xffffffffu, v_active);
         if (v_active) {
-            const int r0 = rs + chunk * G::RB;                    // first row of this chunk
 #pragma unroll 1
-            for (int sub = 0; sub < G::RB / G::UNR; sub++) {
-                // rows rb..rb+UNR-1 arrive; row r completes the outputs y with floor(y*D/N) = r - A.
-                // rb - A = D*t0 + S0 exactly, so everything relative to ybase = N*t0 is static.
-                const int rb = r0 + sub * G::UNR;
+            for (int sub = 0; sub < G::RB / G::UNR; sub++, ybase += N * (G::UNR / D), obase += oblock) {
+                // rows rb..rb+UNR-1 arrive (rb = rs + chunk*RB + sub*UNR); row r completes the outputs y with
+                // floor(y*D/N) = r - A.  rb - A = D*t0 + S0 exactly, so everything relative to ybase = N*t0 is
+                // static; ybase and the output pointer obase advance by one block per iteration.
                 const uint8_t *vrow = vcol + (slot0 + sub * G::UNR) * SWM;   // no ring wrap inside a block
-                const int t0 = (rb - A - G::S0) / D;               // exact division (also for negative values)
-                const int ybase = N * t0;
-                uint8_t *obase = ocol + (long long)(ybase - p.out_row0) * opitch;
                 uint32_t fixrows = 0;                              // bit per output row: recompute this thread's word exactly
                 const bool interior = (ybase >= ys) && (ybase + G::YSPAN <= ye);
                 auto body = [&](auto check_tag) {
