@@ -153,6 +153,112 @@ def run_reference_cpu(steps, warmup, threads=None):
             "seconds": dt, "ms_per_step": dt / steps * 1e3}
 
 
+def run_bands(args, rank, local_rank, world):
+    """BASELINE configs[4]: one 16384x16384 RGB8 image upscaled x1.7 (17/10, out = floor(in*17/10)),
+    output rows split into one band per GPU, each GPU holding only its own input rows + halo.
+    Strong scaling: the image is fixed, value = its output pixels / max-over-ranks step time."""
+    import numpy as np
+    import torch
+    import lanczos_hls_b200 as lz
+    from lanczos_hls_b200.sharding import band_range
+
+    S = args.band_size
+    iw = ih = S
+    ow = oh = S * 17 // 10
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    desc = lz.make_desc(iw, ih, ow, oh, 3, 3, 17, 10)
+    r0, r1 = band_range(oh, rank, world)
+    in0, inn = lz.band_input_rows(desc, r0, r1 - r0)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    yy = torch.arange(in0, in0 + inn, device=dev, dtype=torch.float32).view(inn, 1, 1)
+    xx = torch.arange(iw, device=dev, dtype=torch.float32).view(1, iw, 1)
+    cc = torch.arange(3, device=dev, dtype=torch.float32).view(1, 1, 3)
+    d_in = (128 + 90 * torch.sin(0.05 * xx + cc) * torch.cos(0.037 * yy)
+            + torch.randint(-8, 8, (inn, iw, 3), device=dev, generator=g)).clamp_(0, 255).to(torch.uint8)
+    d_out = torch.empty((r1 - r0, ow, 3), dtype=torch.uint8, device=dev)
+
+    def step():
+        lz.upscale_band_device(desc, d_in, d_out, r0, r1 - r0, in0, inn)
+
+    step()
+    torch.cuda.synchronize()
+    st = lz.stats()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = t.item() / args.steps
+
+    # end to end: the band's input rows from pinned host memory, the band's output rows back to it
+    hin = lz.PinnedBuffer(inn * iw * 3)
+    hout = lz.PinnedBuffer((r1 - r0) * ow * 3)
+    hin.array[:] = d_in.reshape(-1).cpu().numpy()
+    h_in_t = torch.from_numpy(hin.array).view(inn, iw, 3)
+    h_out_t = torch.from_numpy(hout.array).view(r1 - r0, ow, 3)
+    e_steps = max(2, min(args.steps, 4))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        d_in.copy_(h_in_t, non_blocking=True)
+        step()
+        h_out_t.copy_(d_out, non_blocking=True)
+    torch.cuda.synchronize()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_hbm_peak()
+    algo = iw * ih * 3 + ow * oh * 3
+    achieved = algo / world / (ms_per_step * 1e-3) / 1e9      # per GPU (bands are equal to within one row)
+    line = {
+        "metric": "output Mpix/s", "value": ow * oh / (ms_per_step * 1e-3) / 1e6, "unit": "Mpix/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32 (f64 exact re-evaluation near integers)", "data": "synthetic",
+        "config": {"workload": f"single {iw}x{ih} -> {ow}x{oh} RGB8 x1.7 (17/10) image, one row band per GPU with halo rows "
+                               "(BASELINE configs[4])", "content": "smooth", "kernel_id": st["kernel_id"],
+                   "l2": f"inputs larger than L2: {algo / world / 1e6:.0f} MB streamed per GPU per step"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "kernel": "main kernel of the band (whole step: includes the top-rows kernel in band 0)",
+                     "algorithmic_bytes_per_launch": algo / world},
+        "cpu_baseline": None,
+        "e2e": {"value": ow * oh * e_steps / te.item() / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": inn * iw * 3,
+                "d2h_bytes_per_step": (r1 - r0) * ow * 3, "steps": e_steps,
+                "api": "pinned host band -> lanczos_b200_upscale_band -> pinned host band"},
+        "gpu_launches": st["kernel_launches"] * args.steps, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -160,7 +266,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU per step (0 = workload default)")
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 = headline (BASELINE configs[1])")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c5"],
+                    help="c2 = headline (BASELINE configs[1]); c5 = one large image in row bands (BASELINE configs[4])")
+    ap.add_argument("--band-size", type=int, default=16384, help="c5: input side length")
     ap.add_argument("--content", default="smooth", choices=["noise", "smooth"],
                     help="smooth = SURVEY 8d(ii) image-like content (default); noise = 8d(i) uniform noise, the worst "
                          "case for the exact re-evaluation path (reported as worst_case in the JSON line)")
@@ -170,6 +278,15 @@ def main():
     ap.add_argument("--flags", type=int, default=0)
     args = ap.parse_args()
     global IN_W, IN_H, OUT_W, OUT_H, CH, A, SN, SD, DEF_FRAMES, WORKLOAD, ALGO_BYTES_PER_FRAME, OUT_PX_PER_FRAME
+    if args.workload == "c5" and args.impl == "ours":
+        _rank, _lrank, _world = (int(os.environ.get(k, "0")) for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"))
+        if max(_world, 1) == 1 and args.gpus > 1:
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+            os.execv(sys.executable, cmd)
+        return run_bands(args, _rank, _lrank, max(_world, 1))
+    if args.workload == "c5":
+        args.workload = "c2"          # the reference arm always samples the headline workload
     IN_W, IN_H, OUT_W, OUT_H, CH, A, SN, SD, DEF_FRAMES, WORKLOAD = WORKLOADS[args.workload]
     ALGO_BYTES_PER_FRAME = IN_W * IN_H * CH + OUT_W * OUT_H * CH
     OUT_PX_PER_FRAME = OUT_W * OUT_H

@@ -316,7 +316,9 @@ lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
     uint16_t *wq = sm.fixq[tid >> 5], *wb = sm.fixb[tid >> 5];
     // running output pointer of the V pass: row (ybase - out_row0) of this thread's column, advanced per block
     const int t0_first = (rs - A - G::S0) / D;                 // exact division (also for negative values)
-    uint8_t *obase = ocol + (long long)(N * t0_first - p.out_row0) * opitch;
+    // uniform part of the output address (row ybase of the strip) + a 32-bit per-thread offset
+    uint8_t *obase_u = out_frame + obyte0 + (long long)(N * t0_first - p.out_row0) * opitch;
+    const uint32_t ocoff = 4u * (uint32_t)tid, opitch32 = (uint32_t)opitch;
     const long long oblock = (long long)(N * (G::UNR / D)) * opitch;   // output rows per V block
     int ybase = N * t0_first;
 
@@ -444,7 +446,8 @@ lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
         const unsigned vmask = __ballot_sync(0xffffffffu, v_active);
         if (v_active) {
 #pragma unroll 1
-            for (int sub = 0; sub < G::RB / G::UNR; sub++, ybase += N * (G::UNR / D), obase += oblock) {
+            for (int sub = 0; sub < G::RB / G::UNR; sub++, ybase += N * (G::UNR / D), obase_u += oblock) {
+                uint8_t *obase = obase_u + ocoff;
                 // rows rb..rb+UNR-1 arrive (rb = rs + chunk*RB + sub*UNR); row r completes the outputs y with
                 // floor(y*D/N) = r - A.  rb - A = D*t0 + S0 exactly, so everything relative to ybase = N*t0 is
                 // static; ybase and the output pointer obase advance by one block per iteration.
@@ -494,7 +497,7 @@ lanczos_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                                 q = quantise4(a0.x, a0.y, a1.x, a1.y);
                                 fixrows |= (q != quantise4(b0.x, b0.y, b1.x, b1.y) ? 1u : 0u) << yy;
                             }
-                            *reinterpret_cast<uint32_t *>(obase + (long long)yy * opitch) = q;
+                            *reinterpret_cast<uint32_t *>(obase_u + (ocoff + (uint32_t)yy * opitch32)) = q;
                         }
                     }
                 };
@@ -655,7 +658,7 @@ int launch_fast(const KParams &k, const FastHostTables &t, int *kernel_id, cudaS
     if (k.in_pitch % 16 != 0 || k.out_pitch % 4 != 0) return -1;
     if ((reinterpret_cast<uintptr_t>(k.in) & 15) != 0 || (reinterpret_cast<uintptr_t>(k.out) & 3) != 0) return -1;
     if (k.n_frames > 1 && (k.in_frame_stride % 16 != 0 || k.out_frame_stride % 4 != 0)) return -1;
-    if (k.out_rows >= 65536) return -1;   // list entries hold the row in 16 bits per segment; keep it simple
+    if (k.out_pitch >= (1LL << 26)) return -1;   // V-pass stores use 32-bit offsets inside a block of rows
     const int C = k.channels, A = k.a, N = k.scale_n, D = k.scale_d;
     // tuning knob (tools only): LZB_NT=256 selects 256-thread CTAs with 1024-byte strips
     static const int nt = [] { const char *e = getenv("LZB_NT"); return e ? atoi(e) : 128; }();
