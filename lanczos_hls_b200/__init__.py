@@ -12,6 +12,7 @@ from .api import (  # noqa: F401
     LanczosError,
     FLAG_NO_ALIAS,
     FLAG_FAST_ALIGNED,
+    FLAG_TOLERANCE_1LSB,
     FLAG_GENERIC_KERNEL,
     abi_version,
     alias_rows,

@@ -6,6 +6,7 @@
 // frame batches or row bands as the unit of work, and no collectives.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -188,6 +189,8 @@ int run_device(const DevicePlan &dp, unsigned flags, const uint8_t *d_in, uint8_
     p.i0y = dp.i0y; p.wfy = dp.wfy; p.wdy = dp.wdy;
     p.phase_w = dp.phase_w;
     p.guard = h.guard;
+    p.guard_asc = h.guard_asc;
+    p.guard_outer = h.guard_outer;
     p.alias_rows = h.alias_rows; p.alias_top_row = h.alias_top_row; p.alias_in_rows = h.alias_in_rows;
     p.flags = flags;
     p.strict_counter = g_stats_enabled ? dp.strict_counter : nullptr;
@@ -200,7 +203,10 @@ int run_device(const DevicePlan &dp, unsigned flags, const uint8_t *d_in, uint8_
     if (!(flags & LANCZOS_FLAG_GENERIC_KERNEL)) {
         FastHostTables t{h.phase_w.data(), h.phase_wd.data(), h.align_k.data(), h.x.aligned_exact ? 1 : 0,
                          h.y.aligned_exact ? 1 : 0, h.x.uniform_phase ? 1 : 0, h.y.uniform_phase ? 1 : 0};
-        frc = launch_fast(p, t, &kid, s);
+        // development switch: LZB_IMPL=v5 selects the first-generation specialised kernels
+        const char *impl = getenv("LZB_IMPL");
+        if (!(impl && impl[0] == 'v' && impl[1] == '5')) frc = launch_v6(p, t, &kid, s);
+        if (frc < 0 && !(flags & LANCZOS_FLAG_TOLERANCE_1LSB)) frc = launch_fast(p, t, &kid, s);
     }
     if (frc > 0) return cuda_fail((cudaError_t)frc, "launch_fast");
     cudaError_t e = cudaSuccess;

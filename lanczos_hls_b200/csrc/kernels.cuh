@@ -21,7 +21,8 @@ struct KParams {
     const int32_t *i0x; const float *wfx; const double *wdx;
     const int32_t *i0y; const float *wfy; const double *wdy;
     const float *phase_w;          // [scale_n][taps]
-    float guard;
+    float guard;                   // ascending taps, |.|-sum bound (generic + first-generation kernels)
+    float guard_asc, guard_outer;  // sign-aware bounds: ascending order / outermost taps first (lanczos_v6.cu)
     int alias_rows, alias_top_row, alias_in_rows;
     unsigned flags;
     unsigned long long *strict_counter;  // may be null
@@ -39,6 +40,8 @@ struct FastHostTables {            // host-side views of the plan the specialise
     int uniform_x, uniform_y;      // AxisTables.uniform_phase
 };
 int launch_fast(const KParams &p, const FastHostTables &t, int *kernel_id, cudaStream_t s);
+// Second generation of the same (lanczos_v6.cu): 8-byte V columns, PRMT-spliced copies, scalar constant-bank FFMA.
+int launch_v6(const KParams &p, const FastHostTables &t, int *kernel_id, cudaStream_t s);
 // In-place top rows (full_TB.h:67-77 aliasing), exact double arithmetic.
 int launch_alias_rows(const KParams &p, cudaStream_t s);
 // Fixed-point HLS arithmetic (lanczos_hls.cu), integer scales; lut has a*n+1 entries in units of 2^-bp.

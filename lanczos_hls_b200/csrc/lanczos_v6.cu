@@ -1,0 +1,767 @@
+// lanczos_v6.cu -- specialised fused H->V Lanczos kernels for sm_100a, second generation.
+//
+// What it replaces in the reference (software-path arithmetic, HLS-path structure):
+//   cyclic_buffer/cyclic_buffer.h:4-69  2a(+1)-line cyclic buffer   -> shared-memory ring of H-pass rows
+//   worker.cpp:138-155 ColWorkers::exec (vertical MAC per column)    -> systolic V pass: 2a-1 partial sums per
+//                                                                       column in registers, one FFMA each per row
+//   worker.cpp:225-247 RowWorkers::exec (horizontal MAC)             -> H pass on TMA-staged rows
+//   lanczos.cpp:68-83  process_channel block loop (DATAFLOW)          -> chunk loop: H(c+1) overlaps V(c) through
+//                                                                       mbarriers, no CTA-wide barrier
+//   kernel.cpp:40-58   coefficient LUT                                -> polyphase table in the constant bank
+//   full_TB.h:55-77    the arithmetic that must be matched bit for bit
+//
+// One CTA = one strip of <= VB*NT output byte-columns x one vertical segment, streamed in chunks of RB input rows.
+//   1. TMA (cp.async.bulk.tensor 3-D: x, y, frame; out-of-bounds = 0 = the reference's dropped taps) stages
+//      RB input rows + halo bytes into shared memory, double buffered on mbarriers.
+//   2. H pass (one item per thread and chunk): PH ratio periods of one row.  8-byte conflict-free LDS, bytes ->
+//      fp32 via PRMT + FHADD (fp16-subnormal trick), 2a-tap FFMA chains with constant-bank weights for the
+//      interpolated samples only, smallest weights first (tighter rounding bound).  Phase-0 samples (copies)
+//      never pass through fp32: PRMT splices the raw input bytes next to the F2IP-quantised interpolated
+//      bytes; 16-byte STS into the ring.
+//   3. V pass, systolic: a thread owns VB byte-columns.  Per new ring row: one LDS.64, bytes -> fp32, then every
+//      pending output row of the column takes its next tap (acc[j-1] = fma(x, w, acc[j]): the FFMA's
+//      destination does the window shift, so the loop body is one ratio period and the code stays small enough
+//      for the instruction cache); the row that received its last tap is quantised and stored (STG.64).
+//      The phase-0 "cannot flip" test runs on the fp16x2 pipe with exact small-integer arithmetic
+//      (8*v - 3*(b[-2]+b[+2]) >= 0, a conservative form of plan.cpp's filter).
+// Exactness: sums start at -guard; a sample whose truncation differs between x-guard and x+guard is
+// recomputed with the reference's double arithmetic (full_TB.h:58-63) by the thread that found it.
+// MODE 1 (LANCZOS_FLAG_TOLERANCE_1LSB): the V pass is plain fp32 (no guard, no phase-0 test); the H pass
+// stays exact, so every output byte is within 1 LSB of the reference.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <type_traits>
+#include <cuda.h>
+
+#include "../../include/lanczos_b200.h"
+#include "fast_common.cuh"
+
+namespace lzb {
+
+namespace {
+
+struct V6Params {
+    uint8_t *out;         // output row `out_row0` of frame 0
+    long long out_pitch, out_frame_stride;
+    int in_w, in_h, out_w, out_h;
+    int out_row0, out_rows, in_row0, in_rows;
+    int sw;               // strip width in output bytes (groups * OUT_B)
+    int groups;           // H-pass thread groups per strip row
+    int seg_periods;      // vertical ratio-periods per segment
+    int vperiod0;         // first vertical period covered by the launch (floor(out_row0 / N))
+    const double *wdx, *wdy;  // per-coordinate double weights (exact recomputation, non-uniform phases)
+    float guard_h, guard_v;   // rigorous fp32 error bounds (x1.05) of the two summation orders
+    int uniform_x, uniform_y; // double weights identical for all coordinates of a phase -> wdtab usable
+    int strict_v_identity;    // 0 with LANCZOS_FLAG_FAST_ALIGNED
+    float align_k[8];         // phase-0 "cannot flip" constants
+    int align_ki[8];          // the same, ceil(K * 2^16), for the integer re-check in the slow paths
+    float wtab[32 * 8];       // polyphase table [N][8] (padded to 8 taps), N <= 32, times 2^24
+    double wdtab[8 * 8];      // double polyphase table [N][8] for N <= 8 (valid when uniform_*)
+    unsigned long long *strict_counter;
+};
+
+__host__ __device__ constexpr int cdiv6(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ constexpr int cmax6(int a, int b) { return a > b ? a : b; }
+__host__ __device__ constexpr int lcm2(int d) { return d % 2 == 0 ? d : 2 * d; }
+
+template <int C, int A, int N, int D, int PH, int NT>
+struct Geo6 {
+    static constexpr int THREADS = NT;
+    static constexpr int VB = 8;                        // byte-columns per V thread
+    static constexpr int SW_MAX = VB * NT;              // strip width in output bytes
+    static constexpr int TAPS = 2 * A;
+    static constexpr int IN_B = PH * D * C;             // input bytes owned by one H item
+    static constexpr int OUT_B = PH * N * C;            // output bytes produced by one H item
+    static constexpr int NI = PH * (N - 1) * C;         // interpolated (phase != 0) samples per H item
+    static constexpr int ND = (NI + 3) / 4;             // ... packed 4 per word
+    static constexpr int HALO_L = (A - 1) * C;
+    static constexpr int B_LAST = ((N - 1) * D) / N;
+    static constexpr int HALO_R = cmax6(0, (B_LAST + A + 1 - D) * C);
+    static constexpr int PAD_L = 16 * ((HALO_L + 15) / 16);       // TMA box starts PAD_L bytes left of the strip
+    static constexpr int WIN_B = HALO_L + IN_B + HALO_R;          // bytes one H item reads
+    static constexpr int MIS = (PAD_L - HALO_L) % 8;              // window start inside its first 8-byte unit
+    static constexpr int WIN0 = PAD_L - HALO_L - MIS;             // first 8-byte unit (byte offset) of group 0
+    static constexpr int NW2 = (MIS + WIN_B + 7) / 8;             // 8-byte loads per H item
+    static constexpr int MAX_GROUPS = SW_MAX / OUT_B;
+    static constexpr int BOX_B = 16 * cdiv6(cmax6(PAD_L + MAX_GROUPS * IN_B + HALO_R, WIN0 + (MAX_GROUPS - 1) * IN_B + 8 * NW2), 16);
+    static constexpr int RB = 6;                                  // input rows per chunk
+    static constexpr int REGIONS = 4;                             // ring regions of RB rows: H(c+1) may run while V(c) reads
+    static constexpr int RING = REGIONS * RB;                     // intermediate rows kept in smem
+    static constexpr int STAGE_B = 128 * ((RB * BOX_B + 127) / 128);  // TMA destinations must be 128-byte aligned
+    // the first row pushed by a segment is rs = D*pv0 - A + 1, so (row - A) mod D is static per chunk row
+    static constexpr int S0 = (((1 - 2 * A) % D) + D) % D;
+    static constexpr int U = lcm2(D);                             // rows per V loop iteration (even: filter delay line parity)
+    static constexpr int YROWS = N * RB / D;                      // output rows completed per chunk
+    static constexpr int HROUNDS = (RB * MAX_GROUPS + NT - 1) / NT;
+    static_assert(IN_B % 8 == 0, "H item input must be 8-byte aligned");
+    static_assert(OUT_B % 16 == 0, "H item output must be 16-byte aligned");
+    static_assert(SW_MAX % OUT_B == 0, "strip must hold a whole number of H items");
+    static_assert(RB % U == 0, "chunk must be a whole number of V loop iterations");
+    static_assert(TAPS - 1 <= RB, "tap rows must not reach further back than one ring region");
+    static_assert(BOX_B / 4 <= 256, "TMA box too wide");
+    static_assert(N <= 32, "phase table too large for kernel params");
+    static_assert(YROWS + N * (S0 + A + 1) / D + 2 <= 32, "fix mask (bit per output row) too small");
+    static_assert(ND <= 31, "H fix mask (bit per packed word) too small");
+    static_assert(D <= 2, "phase-0 filter delay line assumes the +-2 rows are phase-0 centres themselves");
+};
+
+// residue s of a completing centre (c = D*t + s): its output rows are N*t + [ylo, yhi)
+template <int N, int D> __host__ __device__ constexpr int ylo6(int s) { return cdiv6(s * N, D); }
+template <int N, int D> __host__ __device__ constexpr int yhi6(int s) { return cdiv6((s + 1) * N, D); }
+template <int N, int D> __host__ __device__ constexpr int cnt6(int s) {   // interpolated (phase != 0) rows among them
+    int n = 0;
+    for (int yr = ylo6<N, D>(s); yr < yhi6<N, D>(s); yr++) n += ((yr * D) % N != 0) ? 1 : 0;
+    return n;
+}
+template <int N, int D, int TAPS> __host__ __device__ constexpr int nslot6() {   // partial sums alive while a row is processed
+    int best = 0;
+    for (int s0 = 0; s0 < D; s0++) {
+        int n = 0;
+        for (int dc = 0; dc < TAPS; dc++) n += cnt6<N, D>((s0 + dc) % D);
+        best = n > best ? n : best;
+    }
+    return best;
+}
+
+template <class G>
+struct __align__(128) Smem6 {
+    uint8_t in[2][G::STAGE_B];            // TMA destinations (double buffered), row lr at lr * BOX_B
+    uint8_t ring[G::RING][G::SW_MAX];     // H-pass results (uint8), row r lives in slot (r - rs) % RING
+    unsigned long long full[2];           // TMA stage filled
+    unsigned long long hdone[2];          // every thread finished the H pass of chunk c (index c & 1)
+    unsigned long long vdone[2];          // every thread finished the V pass of chunk c (index c & 1)
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Four bytes from up to four source words, positions known at compile time after unrolling: one PRMT for
+// the first two distinct sources, one more per further source.
+template <int NSRC>
+__device__ __forceinline__ uint32_t gather4(const uint32_t (&arr)[NSRC], const int (&id)[4], const int (&bp)[4]) {
+    uint32_t res = 0;
+    bool started = false;
+    int done = 0;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        if ((done >> u) & 1) continue;
+        const int ida = id[u];
+        if (!started) {
+            int idb = -1;
+#pragma unroll
+            for (int v = 0; v < 4; v++)
+                if (v > u && id[v] != ida && idb < 0) idb = id[v];
+            uint32_t sel = 0;
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                if (id[v] == ida) { sel |= (uint32_t)bp[v] << (4 * v); done |= 1 << v; }
+                else if (idb >= 0 && id[v] == idb) { sel |= (uint32_t)(4 + bp[v]) << (4 * v); done |= 1 << v; }
+            }
+            res = __byte_perm(arr[ida], idb >= 0 ? arr[idb] : 0u, sel);
+            started = true;
+        } else {
+            uint32_t sel = 0;
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                if (id[v] == ida) { sel |= (uint32_t)(4 + bp[v]) << (4 * v); done |= 1 << v; }
+                else sel |= (uint32_t)v << (4 * v);
+            }
+            res = __byte_perm(res, arr[ida], sel);
+        }
+    }
+    return res;
+}
+
+// summation order of the H-pass chains: outermost (smallest) weights first, the two central taps last
+template <int TAPS> __host__ __device__ constexpr int tap_order6(int i) { return (i & 1) ? TAPS - 1 - i / 2 : i / 2; }
+
+__device__ __forceinline__ uint32_t hmul2_u(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t hfma2_u(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// slow paths: executed by the thread that found a sample in doubt, kept out of line so that the hot loop
+// stays small.  Both restate full_TB.h:58-63 / :71-75 exactly (exact_taps).
+// ---------------------------------------------------------------------------------------------
+struct HFixArgs {
+    const uint8_t *in_row;    // staged input row of the item (byte 0 = ibyte0 - PAD_L)
+    uint8_t *ring_row;        // ring row of the item
+    int gbyte0;               // strip-relative output byte of the item's first byte
+    int obyte0, ibyte0, valid_bytes;
+    uint32_t fix_g, fix_z;
+};
+
+template <int C, int A, int N, int D, int PH, int KM, int PAD_L>
+__device__ __noinline__ int h_fix(const V6Params &p, const HFixArgs a) {
+    constexpr int TAPS = 2 * A;
+    constexpr int NI = PH * (N - 1) * C;
+    int n_strict = 0;
+    auto fix_byte = [&](int b, bool is_copy) {
+        if (a.gbyte0 + b >= a.valid_bytes) return;
+        const int ob = a.obyte0 + a.gbyte0 + b;                  // global output byte column
+        const int xx = ob / C, c = ob - xx * C;
+        const int first = (xx * D) / N - A + 1;                  // first tap pixel (full_TB.h:59)
+        const int ph = (xx * D) % N;
+        const uint8_t *tap0 = a.in_row + PAD_L + first * C + c - a.ibyte0;
+        if (is_copy && phase0_safe<TAPS, KM>(tap0, C, p.align_ki)) return;
+        uint8_t r;
+        if (p.uniform_x && N <= 8) r = exact_taps<TAPS>(tap0, C, [&](int k) { return p.wdtab[ph * 8 + k]; });
+        else r = exact_taps<TAPS>(tap0, C, [&](int k) { return p.wdx[(long long)xx * TAPS + k]; });
+        a.ring_row[b] = r;
+        n_strict++;
+    };
+#pragma unroll 1
+    for (uint32_t m = a.fix_g; m; m &= m - 1) {
+        const int dw = __ffs(m) - 1;
+#pragma unroll 1
+        for (int e = 0; e < 4; e++) {
+            const int s = 4 * dw + e;
+            if (s >= NI) break;
+            const int per = s / ((N - 1) * C), rem = s - per * ((N - 1) * C);
+            fix_byte((per * N + 1) * C + rem, false);
+        }
+    }
+    if (a.fix_z) {
+#pragma unroll 1
+        for (int per = 0; per < PH; per++)
+#pragma unroll 1
+            for (int c = 0; c < C; c++) fix_byte(per * N * C + c, true);
+    }
+    return n_strict;
+}
+
+struct VFixArgs {
+    const uint8_t *col;       // this thread's column in ring row 0
+    uint8_t *ocol;            // this thread's column in output row `ybase`
+    long long opitch;
+    int ybase, rs, nbytes;    // nbytes: bytes of the column inside the image
+    uint32_t rows;            // bit yy: output row ybase + yy
+};
+
+template <int A, int N, int D, int KM, int RING, int SWM, int VB>
+__device__ __noinline__ int v_fix(const V6Params &p, const VFixArgs a) {
+    constexpr int TAPS = 2 * A;
+    int n_strict = 0;
+#pragma unroll 1
+    for (uint32_t m = a.rows; m; m &= m - 1) {
+        const int yy = __ffs(m) - 1;
+        const int y = a.ybase + yy;
+        const int ph = (y * D) % N;
+        const int s0 = ((y * D) / N - A + 1 - a.rs) % RING;       // ring slot of the first tap row (full_TB.h:72)
+        uint8_t *orow = a.ocol + (long long)yy * a.opitch;
+#pragma unroll 1
+        for (int e = 0; e < VB; e++) {
+            if (e >= a.nbytes) break;
+            uint8_t taps_b[TAPS];
+#pragma unroll
+            for (int k = 0; k < TAPS; k++) taps_b[k] = a.col[((s0 + k) % RING) * SWM + e];
+            if (ph == 0 && phase0_safe<TAPS, KM>(taps_b, 1, p.align_ki)) continue;
+            if (p.uniform_y && N <= 8) orow[e] = exact_taps<TAPS>(taps_b, 1, [&](int k) { return p.wdtab[ph * 8 + k]; });
+            else orow[e] = exact_taps<TAPS>(taps_b, 1, [&](int k) { return p.wdy[(long long)y * TAPS + k]; });
+            n_strict++;
+        }
+    }
+    return n_strict;
+}
+
+template <int C, int A, int N, int D, int PH, int KM, int NT, int MODE, bool ST64>
+__global__ void __launch_bounds__(NT, (NT == 96 ? 5 : 4))
+lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ V6Params p) {
+    using G = Geo6<C, A, N, D, PH, NT>;
+    constexpr int TAPS = G::TAPS;
+    constexpr int SWM = G::SW_MAX;
+    constexpr int VB = G::VB;
+    constexpr int CEN = A - 1;                                  // centre tap of a phase-0 sample
+    constexpr int NSLOT = nslot6<N, D, TAPS>();
+    constexpr int CNTMAX = cmax6(1, cmax6(cnt6<N, D>(0), cnt6<N, D>(D - 1)));   // D <= 2
+    constexpr bool FILTER = (MODE == 0) && (KM != 0);
+    static_assert(KM == 0 || (A == 3 && KM == 0x11), "phase-0 row filter is written for the +-2 residues of a = 3");
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    Smem6<G> &sm = *reinterpret_cast<Smem6<G> *>(smem_raw);
+
+    const int tid = threadIdx.x;
+    const int strip = blockIdx.x, seg = blockIdx.y, frame = blockIdx.z;
+    uint8_t *out_frame = p.out + (long long)frame * p.out_frame_stride;
+
+    // horizontal extent
+    const int obyte0 = strip * p.sw;                          // first output byte column of the strip
+    const int row_bytes = p.out_w * C;
+    const int valid_bytes = min(p.sw, row_bytes - obyte0);    // > 0 by construction of the grid
+    const int groups = min(p.groups, (valid_bytes + G::OUT_B - 1) / G::OUT_B);
+    const int ibyte0 = (obyte0 / (N * C)) * (D * C);          // first input byte column of the strip
+    // vertical extent: periods [pv0, pv1) -> output rows [N*pv0, N*pv1), clipped to the band
+    const int pv0 = p.vperiod0 + seg * p.seg_periods;
+    const int y_end_band = p.out_row0 + p.out_rows;
+    const int pv1 = min(pv0 + p.seg_periods, (y_end_band + N - 1) / N);
+    const int ys = max(N * pv0, p.out_row0), ye = min(N * pv1, y_end_band);
+    if (ys >= ye) return;
+    const int rs = D * pv0 - A + 1;                           // first intermediate row pushed
+    const int nrows = D * (pv1 - pv0) + TAPS - 1;             // rows to push
+    const int nchunks = (nrows + G::RB - 1) / G::RB;
+
+    const uint32_t full0 = smem_u32(&sm.full[0]), hdone0 = smem_u32(&sm.hdone[0]), vdone0 = smem_u32(&sm.vdone[0]);
+    if (tid == 0) {
+        mbar_init(full0, 1);
+        mbar_init(full0 + 8, 1);
+        mbar_init(hdone0, NT);
+        mbar_init(hdone0 + 8, NT);
+        mbar_init(vdone0, NT);
+        mbar_init(vdone0 + 8, NT);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    constexpr uint32_t kStageBytes = G::RB * G::BOX_B;
+    auto issue = [&](int chunk) {
+        const uint32_t bar = full0 + 8 * (chunk & 1);
+        mbar_expect_tx(bar, kStageBytes);
+        tma_load_3d(smem_u32(&sm.in[chunk & 1][0]), &in_map, (ibyte0 - G::PAD_L) / 4, rs + chunk * G::RB - p.in_row0, frame, bar);
+    };
+    if (tid == 0) {
+        issue(0);
+        if (nchunks > 1) issue(1);
+    }
+
+    // ------------------------------ H pass of one chunk ------------------------------
+    int n_strict = 0;
+    const float guard_h = p.guard_h, g2h = 2.f * p.guard_h;
+    auto h_pass = [&](int chunk) {
+        const int st = chunk & 1;
+        mbar_wait(full0 + 8 * st, (chunk >> 1) & 1);
+        const int slot0 = (chunk % G::REGIONS) * G::RB;          // ring slot of this chunk's first row
+#pragma unroll 1
+        for (int hr = 0; hr < G::HROUNDS; hr++) {
+            const int item = hr * NT + tid;
+            if (item >= G::RB * groups) break;
+            const int lr = item / groups, g = item - lr * groups;
+            const uint8_t *srow = &sm.in[st][lr * G::BOX_B];
+            const uint2 *src = reinterpret_cast<const uint2 *>(srow + G::WIN0 + g * G::IN_B);
+            // srcw[0 .. 2*NW2): raw input words; srcw[2*NW2 ..): quantised interpolated samples, 4 per word
+            uint32_t srcw[2 * G::NW2 + G::ND];
+            float f[G::NW2 * 8];
+#pragma unroll
+            for (int wi = 0; wi < G::NW2; wi++) {
+                const uint2 w = src[wi];
+                srcw[2 * wi] = w.x;
+                srcw[2 * wi + 1] = w.y;
+                word_to_f32x4(w.x, f[8 * wi], f[8 * wi + 1], f[8 * wi + 2], f[8 * wi + 3]);
+                word_to_f32x4(w.y, f[8 * wi + 4], f[8 * wi + 5], f[8 * wi + 6], f[8 * wi + 7]);
+            }
+            // window byte k (k = 0 is HALO_L bytes left of the item's own input) = f[MIS + k] * 2^24
+            uint32_t fix_g = 0;        // bit per packed word of interpolated samples: truncation in doubt
+            // interpolated samples, in output order, packed 4 per word
+#pragma unroll
+            for (int dw = 0; dw < G::ND; dw++) {
+                float xa[4], xb[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int s = 4 * dw + e;
+                    if (s < G::NI) {
+                        const int per = s / ((N - 1) * C), rem = s % ((N - 1) * C);
+                        const int r = 1 + rem / C, c = rem % C;
+                        const int ph = (r * D) % N;
+                        const int base = (per * D + (r * D) / N) * C + c;   // window index of tap 0
+                        float acc = -guard_h;
+#pragma unroll
+                        for (int i = 0; i < TAPS; i++) {
+                            const int k = tap_order6<TAPS>(i);
+                            acc = fmaf(f[G::MIS + base + k * C], p.wtab[ph * 8 + k], acc);
+                        }
+                        xa[e] = acc;
+                        xb[e] = acc + g2h;
+                    } else {
+                        xa[e] = xb[e] = 0.f;
+                    }
+                }
+                const uint32_t qa = quantise4(xa[0], xa[1], xa[2], xa[3]);
+                const uint32_t qb = quantise4(xb[0], xb[1], xb[2], xb[3]);
+                srcw[2 * G::NW2 + dw] = qa;
+                if (qa != qb) fix_g |= 1u << dw;
+            }
+            // phase-0 samples are copies of the centre tap; "cannot flip" filter of plan.cpp:
+            // v - sum K_k*b_k >= 0 over the negative residues -> the reference returns v as well
+            uint32_t zor = 0;
+            if (KM != 0) {
+#pragma unroll
+                for (int per = 0; per < PH; per++)
+#pragma unroll
+                    for (int c = 0; c < C; c++) {
+                        const int base = per * D * C + c;
+                        float z = f[G::MIS + base + CEN * C];
+#pragma unroll
+                        for (int k = 0; k < TAPS; k++)
+                            if ((KM >> k) & 1) z = fmaf(f[G::MIS + base + k * C], -p.align_k[k], z);
+                        zor |= __float_as_uint(z);
+                    }
+            }
+            // splice copies (raw input bytes) and interpolated bytes into the output words
+            uint8_t *drow = &sm.ring[slot0 + lr][g * G::OUT_B];
+            uint4 *dst = reinterpret_cast<uint4 *>(drow);
+#pragma unroll
+            for (int v4 = 0; v4 < G::OUT_B / 16; v4++) {
+                uint32_t o4[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int ow = 4 * v4 + q;
+                    int id[4], bp[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const int o = 4 * ow + e;
+                        const int px = o / C, c = o % C;
+                        const int per = px / N, r = px % N;
+                        if (r == 0) {
+                            const int bi = G::MIS + (per * D + CEN) * C + c;
+                            id[e] = bi / 4;
+                            bp[e] = bi % 4;
+                        } else {
+                            const int s = per * (N - 1) * C + (r - 1) * C + c;
+                            id[e] = 2 * G::NW2 + s / 4;
+                            bp[e] = s % 4;
+                        }
+                    }
+                    o4[q] = gather4(srcw, id, bp);
+                }
+                dst[v4] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+            }
+            // rare: a truncation in doubt or a phase-0 sample that may flip -> this thread looks again
+            if (fix_g != 0 || (int)zor < 0) {
+                HFixArgs a;
+                a.in_row = srow; a.ring_row = drow; a.gbyte0 = g * G::OUT_B;
+                a.obyte0 = obyte0; a.ibyte0 = ibyte0; a.valid_bytes = valid_bytes;
+                a.fix_g = fix_g; a.fix_z = zor >> 31;
+                n_strict += h_fix<C, A, N, D, PH, KM, G::PAD_L>(p, a);
+            }
+        }
+        mbar_arrive(hdone0 + 8 * (chunk & 1));
+    };
+
+    // ------------------------------ V-pass state ------------------------------
+    // partial sums of the output rows that are still collecting taps (value * 1, pixel units)
+    float acc[NSLOT][VB];
+#pragma unroll
+    for (int j = 0; j < NSLOT; j++)
+#pragma unroll
+        for (int i = 0; i < VB; i++) acc[j][i] = 0.f;
+    // phase-0 filter delay line (fp16x2 words of the bytes 2 phase-0 rows back, and the same times 8*2^12)
+    constexpr int ZD = (D == 1) ? 2 : 1;                       // D = 1: rows r-1 and r-2 are both centres
+    uint32_t za[ZD][VB / 2], zA[ZD][VB / 2];
+#pragma unroll
+    for (int j = 0; j < ZD; j++)
+#pragma unroll
+        for (int i = 0; i < VB / 2; i++) za[j][i] = zA[j][i] = 0u;
+    const bool v_active = VB * tid < valid_bytes;
+    const bool v_second = VB * tid + 4 < valid_bytes;          // second word of the column inside the image (only !ST64)
+    const float guard_v = MODE == 0 ? p.guard_v : 0.f, g2v = 2.f * p.guard_v;
+    const long long opitch = p.out_pitch;
+    const uint8_t *vcol = &sm.ring[0][VB * tid];               // this thread's column of the ring
+    const int t0_first = (rs - A - G::S0) / D;                 // exact division (also for negative values)
+    int ybase = N * t0_first;                                  // output row of bit 0 of `fixrows` for the current chunk
+    uint8_t *ocol = out_frame + obyte0 + VB * tid + (long long)(ybase - p.out_row0) * opitch;   // column in row ybase
+    uint32_t fixrows = 0;                                      // bit yy: look at output row ybase + yy again
+
+    auto v_pass = [&](int chunk) {
+        const int bslot = (chunk % G::REGIONS) * G::RB;
+        const uint8_t *vrow = vcol + bslot * SWM;
+        // the centre tap row of a phase-0 output lies A rows back: in the previous region for the first A rows
+        const int wrapoff = (bslot == 0) ? G::RING * SWM : 0;
+        const bool interior = (ybase >= ys) && (ybase + G::YROWS + N <= ye);
+        auto body = [&](auto check_tag) {
+            constexpr bool CHECK = decltype(check_tag)::value;
+#pragma unroll 1
+            for (int it = 0; it < G::RB / G::U; it++) {
+                const uint8_t *vit = vrow + it * (G::U * SWM);
+                uint8_t *oit = ocol + (long long)(it * (N * G::U / D)) * opitch;
+                const int yit = ybase + it * (N * G::U / D);
+#pragma unroll
+                for (int u = 0; u < G::U; u++) {
+                    const int s0 = (G::S0 + u) % D, tq = (G::S0 + u) / D;   // completing centre = D*(t + tq) + s0
+                    const int cnt0 = cnt6<N, D>(s0);
+                    const uint2 w = *reinterpret_cast<const uint2 *>(vit + u * SWM);
+                    const uint32_t h0 = __byte_perm(w.x, 0u, 0x4140), h1 = __byte_perm(w.x, 0u, 0x4342);
+                    const uint32_t h2 = __byte_perm(w.y, 0u, 0x4140), h3 = __byte_perm(w.y, 0u, 0x4342);
+                    float x[VB];
+                    x[0] = h2_lo_to_f32(h0); x[1] = h2_hi_to_f32(h0); x[2] = h2_lo_to_f32(h1); x[3] = h2_hi_to_f32(h1);
+                    x[4] = h2_lo_to_f32(h2); x[5] = h2_hi_to_f32(h2); x[6] = h2_lo_to_f32(h3); x[7] = h2_hi_to_f32(h3);
+                    // ---- systolic step: every pending output row takes its next tap from this row ----
+                    float res[CNTMAX][VB];
+                    {
+                        int q = 0;
+#pragma unroll
+                        for (int dc = 0; dc < TAPS; dc++) {
+                            const int sdc = (s0 + dc) % D;
+                            const int k = TAPS - 1 - dc;
+#pragma unroll
+                            for (int yr = ylo6<N, D>(sdc); yr < yhi6<N, D>(sdc); yr++) {
+                                const int ph = (yr * D) % N;
+                                if (ph == 0) continue;
+#pragma unroll
+                                for (int i = 0; i < VB; i++) {
+                                    const float wk = p.wtab[ph * 8 + k];
+                                    if (dc == 0) res[q][i] = fmaf(x[i], wk, acc[q][i]);
+                                    else if (dc < TAPS - 1) acc[q - cnt0][i] = fmaf(x[i], wk, acc[q][i]);
+                                    else acc[q - cnt0][i] = fmaf(x[i], wk, -guard_v);
+                                }
+                                q++;
+                            }
+                        }
+                    }
+                    // ---- phase-0 "cannot flip" test, exact small-integer arithmetic on the fp16x2 pipe ----
+                    // this row r is a phase-0 centre iff (s0 + A) % D == 0; with b = bytes * 2^-24 (fp16 subnormals):
+                    //   zpost(r-2) = 8*v[r-2] - 3*b[r]  and  zpre(r) = 8*v[r] - 3*b[r-2], both times 2^-12, both exact
+                    //   (|.| <= 2040 < 2^11).  K = 3/8 >= plan.cpp's K_k: negative means "may flip".
+                    if (FILTER && (s0 + A) % D == 0) {
+                        const int zs = (ZD == 2) ? (u & 1) : 0;       // D = 1: slot of row r-2 = slot this row overwrites
+                        const uint32_t kQ = 0x78007800u;              // 32768 = 8 * 2^12 (fp16x2)
+                        const uint32_t kP = 0xF200F200u;              // -12288 = -3 * 2^12
+                        const uint32_t hn[4] = {h0, h1, h2, h3};
+                        uint32_t zpost = 0, zpre = 0;
+#pragma unroll
+                        for (int i = 0; i < VB / 2; i++) {
+                            const uint32_t An = hmul2_u(hn[i], kQ);
+                            zpost |= hfma2_u(hn[i], kP, zA[zs][i]);
+                            zpre |= hfma2_u(za[zs][i], kP, An);
+                            za[zs][i] = hn[i];
+                            zA[zs][i] = An;
+                        }
+                        // output rows of centre r-2 = c+A-2 and of centre r = c+A, relative to ybase (static)
+                        const int yy_post = N * (it * G::U + G::S0 + u + A - 2) / D;
+                        const int yy_pre = N * (it * G::U + G::S0 + u + A) / D;
+                        if (zpost & 0x80008000u) fixrows |= 1u << yy_post;
+                        if (zpre & 0x80008000u) fixrows |= 1u << yy_pre;
+                    }
+                    // ---- rows that received their last tap ----
+                    {
+                        int q = 0;
+#pragma unroll
+                        for (int yr = ylo6<N, D>(s0); yr < yhi6<N, D>(s0); yr++) {
+                            const int ph = (yr * D) % N;
+                            const int yoff = N * tq + yr;                 // output row relative to yit
+                            uint2 qv;
+                            bool doubt = false;
+                            if (ph == 0) {
+                                const int back = u - A;                   // centre row relative to this iteration's first row
+                                const uint8_t *crow = vit + back * SWM;
+                                if (back < 0 && it * G::U + back < 0) crow += wrapoff;   // previous ring region
+                                qv = *reinterpret_cast<const uint2 *>(crow);
+                            } else {
+                                qv.x = quantise4(res[q][0], res[q][1], res[q][2], res[q][3]);
+                                qv.y = quantise4(res[q][4], res[q][5], res[q][6], res[q][7]);
+                                if (MODE == 0) {
+                                    const uint32_t bx = quantise4(res[q][0] + g2v, res[q][1] + g2v, res[q][2] + g2v, res[q][3] + g2v);
+                                    const uint32_t by = quantise4(res[q][4] + g2v, res[q][5] + g2v, res[q][6] + g2v, res[q][7] + g2v);
+                                    doubt = (qv.x != bx) || (qv.y != by);
+                                }
+                                q++;
+                            }
+                            const int y = yit + yoff;
+                            if (CHECK && (y < ys || y >= ye)) continue;
+                            if (MODE == 0 && doubt) fixrows |= 1u << (it * (N * G::U / D) + yoff);
+                            uint8_t *orow = oit + (long long)yoff * opitch;
+                            if (ST64) {
+                                *reinterpret_cast<uint2 *>(orow) = qv;
+                            } else {
+                                *reinterpret_cast<uint32_t *>(orow) = qv.x;
+                                if (v_second) *reinterpret_cast<uint32_t *>(orow + 4) = qv.y;
+                            }
+                        }
+                    }
+                }
+            }
+        };
+        if (interior) body(std::false_type{}); else body(std::true_type{});
+        if (MODE == 0) {
+            // rows [ylo(S0), ylo(S0) + YROWS) relative to ybase were stored in this chunk; later bits wait
+            constexpr uint32_t kDone = (uint32_t)((1ull << (ylo6<N, D>(G::S0) + G::YROWS)) - 1ull);
+            uint32_t todo = fixrows & kDone;
+            fixrows = (fixrows & ~kDone) >> G::YROWS;
+            if (!p.strict_v_identity) {      // LANCZOS_FLAG_FAST_ALIGNED: phase-0 rows stay plain copies
+                uint32_t ph0rows = 0;
+#pragma unroll
+                for (int yy = 0; yy < 32; yy++)
+                    if ((yy * D) % N == 0) ph0rows |= 1u << yy;
+                todo &= ~ph0rows;
+            }
+            if (todo) {
+                // rows outside [ys, ye) were never stored (their bits can only come from the phase-0 test)
+                uint32_t inrange = 0;
+                if (!interior) {
+#pragma unroll 1
+                    for (int yy = 0; yy < 32; yy++)
+                        if (ybase + yy >= ys && ybase + yy < ye) inrange |= 1u << yy;
+                    todo &= inrange;
+                }
+                if (todo) {
+                    VFixArgs a;
+                    a.col = vcol; a.ocol = ocol; a.opitch = opitch; a.ybase = ybase; a.rs = rs;
+                    a.nbytes = min(VB, valid_bytes - VB * tid);
+                    a.rows = todo;
+                    n_strict += v_fix<A, N, D, KM, G::RING, SWM, VB>(p, a);
+                }
+            }
+        }
+        ybase += G::YROWS;
+        ocol += (long long)G::YROWS * opitch;
+    };
+
+    // ------------------------------ pipeline ------------------------------
+    // iteration c: H(c+1) [needs V(c-2) finished by everyone: ring region (c+1) % 4 is free], then V(c)
+    // [needs H(c) finished by everyone].  Both conditions were signalled one phase earlier, so the waits are
+    // normally already satisfied: no CTA-wide barrier in the loop.
+    for (int chunk = -1; chunk < nchunks; chunk++) {
+        if (chunk + 1 < nchunks) {
+            if (chunk >= 2) mbar_wait(vdone0 + 8 * (chunk & 1), ((chunk - 2) >> 1) & 1);
+            h_pass(chunk + 1);
+        }
+        if (chunk < 0) continue;
+        mbar_wait(hdone0 + 8 * (chunk & 1), (chunk >> 1) & 1);
+        // every thread has read TMA stage (chunk & 1): refill it with chunk + 2
+        if (tid == 0 && chunk + 2 < nchunks) issue(chunk + 2);
+        if (v_active) v_pass(chunk);
+        mbar_arrive(vdone0 + 8 * (chunk & 1));
+    }
+    if (p.strict_counter && n_strict) atomicAdd(p.strict_counter, (unsigned long long)n_strict);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+template <int C, int A, int N, int D, int PH, int KM, int NT, int MODE, bool ST64>
+int launch_v6_one(const KParams &k, const FastHostTables &t, cudaStream_t s) {
+    using G = Geo6<C, A, N, D, PH, NT>;
+    EncodeFn encode = get_encode();
+    if (!encode) return -1;
+    const int row_bytes = k.out_w * C;
+    // strip width: a multiple of OUT_B (<= 8*NT bytes) whose input start stays 16-byte aligned for every
+    // strip (TMA needs a 16-byte aligned box start), wasting the fewest threads
+    int best_groups = 0;
+    double best_eff = -1;
+    for (int gr = G::MAX_GROUPS; gr >= 1; gr--) {
+        if ((gr * G::IN_B) % 16 != 0) continue;
+        const int sw_c = gr * G::OUT_B;
+        const int strips_c = (row_bytes + sw_c - 1) / sw_c;
+        const double eff = (double)row_bytes / ((double)strips_c * G::SW_MAX);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best_groups = gr; }
+    }
+    if (best_groups == 0) return -1;
+    const int sw = best_groups * G::OUT_B;
+    const int strips = (row_bytes + sw - 1) / sw;
+    const int vperiod0 = k.out_row0 / N;
+    const int vperiods = (k.out_row0 + k.out_rows + N - 1) / N - vperiod0;
+    // vertical segments: every segment re-runs 2a-1 warm-up rows, every partial last wave idles SMs.
+    // Pick the count that minimises (waves) x (rows per segment + warm-up).
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    auto kern = lanczos_v6_kernel<C, A, N, D, PH, KM, NT, MODE, ST64>;
+    const size_t smem = sizeof(Smem6<G>) + 128;
+    static bool attr_set[64] = {};
+    static int ctas_per_sm[64] = {};
+    if (!attr_set[dev & 63]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NT, smem) != cudaSuccess || nb < 1) nb = 4;
+        ctas_per_sm[dev & 63] = nb;
+        attr_set[dev & 63] = true;
+    }
+    const long long slots = (long long)ctas_per_sm[dev & 63] * sms;
+    const long long cols = (long long)strips * k.n_frames;
+    const int max_segs = std::max(1, vperiods / std::max(1, (2 * G::RB) / D));
+    int segs = 1;
+    double best_cost = 1e300;
+    static const int force_segs = [] { const char *e = getenv("LZB_SEGS"); return e ? atoi(e) : 0; }();
+    for (int sg = 1; sg <= std::min(max_segs, 256); sg++) {
+        const int per = (vperiods + sg - 1) / sg;
+        const int sg_eff = (vperiods + per - 1) / per;
+        const double rows = (double)per * D + 2 * A - 1 + 0.5 * G::RB;      // + pipeline fill
+        const double waves = std::ceil((double)(cols * sg_eff) / (double)slots);
+        // a wave that is not full still costs a full wave unless it is the only one
+        const double cost = (cols * sg_eff <= slots) ? rows * 1.0 : rows * waves;
+        if (cost < best_cost - 1e-9) { best_cost = cost; segs = sg_eff; }
+    }
+    if (force_segs > 0) segs = std::min(force_segs, max_segs);
+    int seg_periods = (vperiods + segs - 1) / segs;
+    segs = (vperiods + seg_periods - 1) / seg_periods;
+
+    CUtensorMap map;
+    const cuuint64_t dims[3] = {(cuuint64_t)(k.in_w * C / 4), (cuuint64_t)k.in_rows, (cuuint64_t)k.n_frames};
+    const cuuint64_t strides[2] = {(cuuint64_t)k.in_pitch, (cuuint64_t)(k.n_frames > 1 ? k.in_frame_stride : k.in_pitch * k.in_rows)};
+    const cuuint32_t box[3] = {(cuuint32_t)(G::BOX_B / 4), (cuuint32_t)G::RB, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    if (encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t *>(k.in), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return -1;
+
+    V6Params p{};
+    p.out = k.out;
+    p.out_pitch = k.out_pitch;
+    p.out_frame_stride = k.out_frame_stride;
+    p.in_w = k.in_w; p.in_h = k.in_h; p.out_w = k.out_w; p.out_h = k.out_h;
+    p.out_row0 = k.out_row0; p.out_rows = k.out_rows; p.in_row0 = k.in_row0; p.in_rows = k.in_rows;
+    p.sw = sw; p.groups = best_groups; p.seg_periods = seg_periods; p.vperiod0 = vperiod0;
+    p.wdx = k.wdx; p.wdy = k.wdy;
+    p.guard_h = k.guard_outer; p.guard_v = k.guard_asc;
+    p.uniform_x = t.uniform_x; p.uniform_y = t.uniform_y;
+    p.strict_v_identity = (k.flags & LANCZOS_FLAG_FAST_ALIGNED) ? 0 : 1;
+    for (int i = 0; i < 8; i++) p.align_k[i] = i < 2 * A ? t.align_k[i] : 0.f;
+    for (int i = 0; i < 8; i++) p.align_ki[i] = (int)std::ceil((double)p.align_k[i] * 65536.0 * 1.0001);
+    for (int ph = 0; ph < N; ph++)
+        for (int q = 0; q < 8; q++) p.wtab[ph * 8 + q] = q < 2 * A ? t.phase_w[ph * 2 * A + q] * 16777216.f : 0.f;  // x 2^24, see kPixUnscale
+    for (int ph = 0; ph < N && ph < 8; ph++)
+        for (int q = 0; q < 8; q++) p.wdtab[ph * 8 + q] = q < 2 * A ? t.phase_wd[ph * 2 * A + q] : 0.0;
+    p.strict_counter = k.strict_counter;
+
+    dim3 grid(strips, segs, k.n_frames);
+    kern<<<grid, NT, smem, s>>>(map, p);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+// Returns 0 on launch, >0 cudaError, -1 when no specialised kernel applies (caller falls back).
+int launch_v6(const KParams &k, const FastHostTables &t, int *kernel_id, cudaStream_t s) {
+    // layout requirements of the TMA map and of the 32-bit/64-bit/128-bit accesses
+    if ((k.in_w * k.channels) % 4 != 0 || (k.out_w * k.channels) % 4 != 0) return -1;
+    if (k.in_pitch % 16 != 0 || k.out_pitch % 4 != 0) return -1;
+    if ((reinterpret_cast<uintptr_t>(k.in) & 15) != 0 || (reinterpret_cast<uintptr_t>(k.out) & 3) != 0) return -1;
+    if (k.n_frames > 1 && (k.in_frame_stride % 16 != 0 || k.out_frame_stride % 4 != 0)) return -1;
+    const bool st64 = (k.out_w * k.channels) % 8 == 0 && k.out_pitch % 8 == 0 && (reinterpret_cast<uintptr_t>(k.out) & 7) == 0 &&
+                      (k.n_frames <= 1 || k.out_frame_stride % 8 == 0);
+    if (!t.exact_x || !t.exact_y) return -1;     // phase-0 coordinates not exactly integral in double: other kernels
+    const int mode = (k.flags & LANCZOS_FLAG_TOLERANCE_1LSB) ? 1 : 0;
+    const int C = k.channels, A = k.a, N = k.scale_n, D = k.scale_d;
+    // KM: taps whose phase-0 residue is negative (nonzero filter constant); the host table must agree
+    int km = 0;
+    for (int q = 0; q < 2 * A; q++)
+        if (t.align_k[q] != 0.f) km |= 1 << q;
+    // the fp16x2 row filter uses K = 3/8 for every flagged tap
+    for (int q = 0; q < 2 * A; q++)
+        if (t.align_k[q] > 0.374f) return -1;
+#define LZ6_CASE(c, a, n, d, ph, kmask, id)                                                            \
+    if (C == c && A == a && N == n && D == d && km == (kmask)) {                                        \
+        *kernel_id = id;                                                                                \
+        if (mode == 0) return st64 ? launch_v6_one<c, a, n, d, ph, kmask, 96, 0, true>(k, t, s)         \
+                                   : launch_v6_one<c, a, n, d, ph, kmask, 96, 0, false>(k, t, s);       \
+        return st64 ? launch_v6_one<c, a, n, d, ph, kmask, 96, 1, true>(k, t, s)                        \
+                    : launch_v6_one<c, a, n, d, ph, kmask, 96, 1, false>(k, t, s);                      \
+    }
+    // a = 3: sin(2*pi) < 0 in double, so the |d| = 2 taps (k = 0 and k = 4) carry negative residues
+    LZ6_CASE(3, 3, 2, 1, 8, 0x11, 1)
+    LZ6_CASE(4, 3, 2, 1, 6, 0x11, 2)
+    LZ6_CASE(4, 3, 3, 2, 4, 0x11, 3)
+    LZ6_CASE(3, 2, 2, 1, 8, 0x0, 4)
+#undef LZ6_CASE
+    return -1;
+}
+
+}  // namespace lzb

@@ -95,6 +95,26 @@ static int build_axis(AxisTables &t, int out_len, int in_len, int a, int n, int 
             round_err += u * (abs_sum + 1.0);
         }
         t.fast_err = std::max(t.fast_err, std::max(werr_coord, werr_phase) + round_err);
+        // Tighter bound for the second-generation kernels (phase-table weights, FMA chains from -guard):
+        //  * bytes are >= 0, so a partial sum lies in [255 * sum of negative weights, 255 * sum of positive ones];
+        //  * one FMA rounds by at most half an ulp of its result: 2^(floor(log2 |result|) - 24);
+        //  * the last FMA only matters when the sum is below 256 (anything above is clamped either way);
+        //  * the weight error sum_k b_k (wf_k - w_k) is bounded by 255 * max(sum of positive, sum of negative errors).
+        for (int order = 0; order < 2; order++) {
+            double lo = 0, hi = 0, rerr = 0, dpos = 0, dneg = 0;
+            for (int i = 0; i < taps; i++) {
+                const int k = order == 0 ? i : ((i & 1) ? taps - 1 - i / 2 : i / 2);
+                const double wf = (double)phase_w[(size_t)phase * taps + k];
+                if (wf > 0) hi += 255.0 * wf; else lo += 255.0 * wf;
+                double m = std::max(-lo, hi) + std::ldexp(1.0, -10);     // + the -guard start value
+                if (i == taps - 1) m = std::min(m, 255.999);
+                rerr += std::ldexp(1.0, (int)std::floor(std::log2(m)) - 24);
+                const double dw = wf - t.wd[(size_t)xx * taps + k];
+                if (dw > 0) dpos += dw; else dneg -= dw;
+            }
+            const double e = rerr + 255.0 * std::max(dpos, dneg);
+            if (order == 0) t.err_asc = std::max(t.err_asc, e); else t.err_outer = std::max(t.err_outer, e);
+        }
     }
     return LANCZOS_OK;
 }
@@ -145,6 +165,8 @@ int build_plan(const lanczos_desc *desc, Plan *out) {
     // guard band: 1.25x the rigorous fp32 error bound, never below 2^-14
     const double e = std::max(p.x.fast_err, p.y.fast_err);
     p.guard = (float)std::max(1.25 * e, std::ldexp(1.0, -14));
+    p.guard_asc = (float)(1.0625 * std::max(p.x.err_asc, p.y.err_asc));
+    p.guard_outer = (float)(1.0625 * std::max(p.x.err_outer, p.y.err_outer));
 
     // in-place aliasing of the vertical pass (full_TB.h:67-77): going bottom-up, row xx reads
     // rows first..last; any row i > xx has already been overwritten with final output.

@@ -24,7 +24,9 @@ struct AxisTables {
     std::vector<float> wf;    // [out_len][2a] the same rounded to float (fast path)
     bool aligned_exact = true;  // every phase-0 coordinate has x exactly integral in double
     bool uniform_phase = true;  // wd[xx][k] == phase_wd[phase(xx)][k] bit for bit, for every coordinate
-    double fast_err = 0;        // rigorous bound on |fp32 fast sum - reference double sum|
+    double fast_err = 0;        // rigorous bound on |fp32 fast sum - reference double sum| (ascending taps, |.| sums)
+    double err_asc = 0;         // the same, sign-aware partial sums and binade-exact half-ulps, ascending taps
+    double err_outer = 0;       // ... outermost taps first (lanczos_v6.cu H pass)
 };
 
 struct Plan {
@@ -34,6 +36,7 @@ struct Plan {
     std::vector<float> phase_w;  // [scale_n][2a] float polyphase table (phase p = (xx*D) mod N)
     std::vector<double> phase_wd;  // [scale_n][2a] double, for reports
     float guard = 0;             // |sum - nearest integer| below this -> exact re-evaluation
+    float guard_asc = 0, guard_outer = 0;   // tighter guards of the second-generation kernels (see AxisTables)
     std::vector<float> align_k;  // [2a] phase-0 "cannot flip" filter constants (see plan.cpp)
     // in-place aliasing (full_TB.h:67-77): rows [0,alias_rows) read already-final rows
     int alias_rows = 0;     // K0
