@@ -90,6 +90,7 @@ struct Geo6 {
     static constexpr int REGIONS = 4;                             // ring regions of RB rows: H(c+1) may run while V(c) reads
     static constexpr int RING = REGIONS * RB;                     // intermediate rows kept in smem
     static constexpr int STAGE_B = 128 * ((RB * BOX_B + 127) / 128);  // TMA destinations must be 128-byte aligned
+    static constexpr int STAGES = 4;                              // TMA stages in flight (a stage is refilled 3 chunks ahead)
     // the first row pushed by a segment is rs = D*pv0 - A + 1, so (row - A) mod D is static per chunk row
     static constexpr int S0 = (((1 - 2 * A) % D) + D) % D;
     static constexpr int U = lcm2(D);                             // rows per V loop iteration (even: filter delay line parity)
@@ -127,9 +128,9 @@ template <int N, int D, int TAPS> __host__ __device__ constexpr int nslot6() {  
 
 template <class G>
 struct __align__(128) Smem6 {
-    uint8_t in[2][G::STAGE_B];            // TMA destinations (double buffered), row lr at lr * BOX_B
+    uint8_t in[G::STAGES][G::STAGE_B];    // TMA destinations, row lr at lr * BOX_B
     uint8_t ring[G::RING][G::SW_MAX];     // H-pass results (uint8), row r lives in slot (r - rs) % RING
-    unsigned long long full[2];           // TMA stage filled
+    unsigned long long full[G::STAGES];   // TMA stage filled
     unsigned long long hdone[2];          // every thread finished the H pass of chunk c (index c & 1)
     unsigned long long vdone[2];          // every thread finished the V pass of chunk c (index c & 1)
 };
@@ -175,6 +176,12 @@ __device__ __forceinline__ uint32_t gather4(const uint32_t (&arr)[NSRC], const i
     return res;
 }
 
+// double_to_uint8 (full_TB.h:29-37) on one fp32 value, as F2IP does it: clamp to [0,255], truncate toward zero
+__device__ __forceinline__ uint32_t quantise_f32(float x) {
+    const int i = __float2int_rz(x);
+    return (uint32_t)min(max(i, 0), 255);
+}
+
 // summation order of the H-pass chains: outermost (smallest) weights first, the two central taps last
 template <int TAPS> __host__ __device__ constexpr int tap_order6(int i) { return (i & 1) ? TAPS - 1 - i / 2 : i / 2; }
 
@@ -199,6 +206,7 @@ struct HFixArgs {
     int gbyte0;               // strip-relative output byte of the item's first byte
     int obyte0, ibyte0, valid_bytes;
     uint32_t fix_g, fix_z;
+    float guard;
 };
 
 template <int C, int A, int N, int D, int PH, int KM, int PAD_L>
@@ -213,7 +221,19 @@ __device__ __noinline__ int h_fix(const V6Params &p, const HFixArgs a) {
         const int first = (xx * D) / N - A + 1;                  // first tap pixel (full_TB.h:59)
         const int ph = (xx * D) % N;
         const uint8_t *tap0 = a.in_row + PAD_L + first * C + c - a.ibyte0;
-        if (is_copy && phase0_safe<TAPS, KM>(tap0, C, p.align_ki)) return;
+        if (is_copy) {
+            if (phase0_safe<TAPS, KM>(tap0, C, p.align_ki)) return;
+        } else {
+            // the hot path's fp32 chain again (same order, same weights: same bits): only a sample whose
+            // truncation really is in doubt needs the double evaluation
+            float acc = -a.guard;
+#pragma unroll
+            for (int i = 0; i < TAPS; i++) {
+                const int k = tap_order6<TAPS>(i);
+                acc = fmaf((float)tap0[k * C] * (1.f / 16777216.f), p.wtab[ph * 8 + k], acc);
+            }
+            if (quantise_f32(acc) == quantise_f32(acc + 2.f * a.guard)) return;
+        }
         uint8_t r;
         if (p.uniform_x && N <= 8) r = exact_taps<TAPS>(tap0, C, [&](int k) { return p.wdtab[ph * 8 + k]; });
         else r = exact_taps<TAPS>(tap0, C, [&](int k) { return p.wdx[(long long)xx * TAPS + k]; });
@@ -265,7 +285,14 @@ __device__ __noinline__ int v_fix(const V6Params &p, const VFixArgs a) {
             uint8_t taps_b[TAPS];
 #pragma unroll
             for (int k = 0; k < TAPS; k++) taps_b[k] = a.col[((s0 + k) % RING) * SWM + e];
-            if (ph == 0 && phase0_safe<TAPS, KM>(taps_b, 1, p.align_ki)) continue;
+            if (ph == 0) {
+                if (phase0_safe<TAPS, KM>(taps_b, 1, p.align_ki)) continue;
+            } else {
+                float acc = -p.guard_v;      // the hot path's fp32 chain again (ascending taps: same bits)
+#pragma unroll
+                for (int k = 0; k < TAPS; k++) acc = fmaf((float)taps_b[k] * (1.f / 16777216.f), p.wtab[ph * 8 + k], acc);
+                if (quantise_f32(acc) == quantise_f32(acc + 2.f * p.guard_v)) continue;
+            }
             if (p.uniform_y && N <= 8) orow[e] = exact_taps<TAPS>(taps_b, 1, [&](int k) { return p.wdtab[ph * 8 + k]; });
             else orow[e] = exact_taps<TAPS>(taps_b, 1, [&](int k) { return p.wdy[(long long)y * TAPS + k]; });
             n_strict++;
@@ -309,10 +336,11 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
     const int nrows = D * (pv1 - pv0) + TAPS - 1;             // rows to push
     const int nchunks = (nrows + G::RB - 1) / G::RB;
 
-    const uint32_t full0 = smem_u32(&sm.full[0]), hdone0 = smem_u32(&sm.hdone[0]), vdone0 = smem_u32(&sm.vdone[0]);
+    uint32_t full0 = smem_u32(&sm.full[0]), hdone0 = smem_u32(&sm.hdone[0]), vdone0 = smem_u32(&sm.vdone[0]);
+    // keep the addresses in registers: without this they are re-derived from the CTA's shared window at every use
+    asm volatile("" : "+r"(full0), "+r"(hdone0), "+r"(vdone0));
     if (tid == 0) {
-        mbar_init(full0, 1);
-        mbar_init(full0 + 8, 1);
+        for (int i = 0; i < G::STAGES; i++) mbar_init(full0 + 8 * i, 1);
         mbar_init(hdone0, NT);
         mbar_init(hdone0 + 8, NT);
         mbar_init(vdone0, NT);
@@ -323,29 +351,40 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
 
     constexpr uint32_t kStageBytes = G::RB * G::BOX_B;
     auto issue = [&](int chunk) {
-        const uint32_t bar = full0 + 8 * (chunk & 1);
+        const uint32_t bar = full0 + 8 * (chunk % G::STAGES);
         mbar_expect_tx(bar, kStageBytes);
-        tma_load_3d(smem_u32(&sm.in[chunk & 1][0]), &in_map, (ibyte0 - G::PAD_L) / 4, rs + chunk * G::RB - p.in_row0, frame, bar);
+        tma_load_3d(smem_u32(&sm.in[chunk % G::STAGES][0]), &in_map, (ibyte0 - G::PAD_L) / 4, rs + chunk * G::RB - p.in_row0, frame, bar);
     };
     if (tid == 0) {
-        issue(0);
-        if (nchunks > 1) issue(1);
+        for (int i = 0; i < G::STAGES && i < nchunks; i++) issue(i);
     }
 
     // ------------------------------ H pass of one chunk ------------------------------
     int n_strict = 0;
     const float guard_h = p.guard_h, g2h = 2.f * p.guard_h;
+    // item = round * NT + tid -> (row, group); the first round's mapping is the same for every chunk
+    int h_src0, h_dst0;
+    {
+        const int lr = tid / groups, g = tid - lr * groups;
+        h_src0 = lr * G::BOX_B + G::WIN0 + g * G::IN_B;
+        h_dst0 = lr * SWM + g * G::OUT_B;
+        asm volatile("" : "+r"(h_src0), "+r"(h_dst0));
+    }
     auto h_pass = [&](int chunk) {
-        const int st = chunk & 1;
-        mbar_wait(full0 + 8 * st, (chunk >> 1) & 1);
+        const int st = chunk % G::STAGES;
+        mbar_wait(full0 + 8 * st, (chunk / G::STAGES) & 1);
         const int slot0 = (chunk % G::REGIONS) * G::RB;          // ring slot of this chunk's first row
 #pragma unroll 1
         for (int hr = 0; hr < G::HROUNDS; hr++) {
             const int item = hr * NT + tid;
             if (item >= G::RB * groups) break;
-            const int lr = item / groups, g = item - lr * groups;
-            const uint8_t *srow = &sm.in[st][lr * G::BOX_B];
-            const uint2 *src = reinterpret_cast<const uint2 *>(srow + G::WIN0 + g * G::IN_B);
+            int src_off = h_src0, dst_off = h_dst0;
+            if (hr > 0) {
+                const int lr = item / groups, g = item - lr * groups;
+                src_off = lr * G::BOX_B + G::WIN0 + g * G::IN_B;
+                dst_off = lr * SWM + g * G::OUT_B;
+            }
+            const uint2 *src = reinterpret_cast<const uint2 *>(&sm.in[st][src_off]);
             // srcw[0 .. 2*NW2): raw input words; srcw[2*NW2 ..): quantised interpolated samples, 4 per word
             uint32_t srcw[2 * G::NW2 + G::ND];
             float f[G::NW2 * 8];
@@ -405,7 +444,7 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
                     }
             }
             // splice copies (raw input bytes) and interpolated bytes into the output words
-            uint8_t *drow = &sm.ring[slot0 + lr][g * G::OUT_B];
+            uint8_t *drow = &sm.ring[slot0][dst_off];
             uint4 *dst = reinterpret_cast<uint4 *>(drow);
 #pragma unroll
             for (int v4 = 0; v4 < G::OUT_B / 16; v4++) {
@@ -436,9 +475,10 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
             // rare: a truncation in doubt or a phase-0 sample that may flip -> this thread looks again
             if (fix_g != 0 || (int)zor < 0) {
                 HFixArgs a;
-                a.in_row = srow; a.ring_row = drow; a.gbyte0 = g * G::OUT_B;
+                const int lr = item / groups, g = item - lr * groups;
+                a.in_row = &sm.in[st][lr * G::BOX_B]; a.ring_row = drow; a.gbyte0 = g * G::OUT_B;
                 a.obyte0 = obyte0; a.ibyte0 = ibyte0; a.valid_bytes = valid_bytes;
-                a.fix_g = fix_g; a.fix_z = zor >> 31;
+                a.fix_g = fix_g; a.fix_z = zor >> 31; a.guard = guard_h;
                 n_strict += h_fix<C, A, N, D, PH, KM, G::PAD_L>(p, a);
             }
         }
@@ -452,13 +492,13 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
     for (int j = 0; j < NSLOT; j++)
 #pragma unroll
         for (int i = 0; i < VB; i++) acc[j][i] = 0.f;
-    // phase-0 filter delay line (fp16x2 words of the bytes 2 phase-0 rows back, and the same times 8*2^12)
+    // phase-0 filter delay line: fp16x2 words 8 * bytes * 2^-12 of the phase-0 rows 2 rows back
     constexpr int ZD = (D == 1) ? 2 : 1;                       // D = 1: rows r-1 and r-2 are both centres
-    uint32_t za[ZD][VB / 2], zA[ZD][VB / 2];
+    uint32_t zA[ZD][VB / 2];
 #pragma unroll
     for (int j = 0; j < ZD; j++)
 #pragma unroll
-        for (int i = 0; i < VB / 2; i++) za[j][i] = zA[j][i] = 0u;
+        for (int i = 0; i < VB / 2; i++) zA[j][i] = 0u;
     const bool v_active = VB * tid < valid_bytes;
     const bool v_second = VB * tid + 4 < valid_bytes;          // second word of the column inside the image (only !ST64)
     const float guard_v = MODE == 0 ? p.guard_v : 0.f, g2v = 2.f * p.guard_v;
@@ -477,11 +517,16 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
         const bool interior = (ybase >= ys) && (ybase + G::YROWS + N <= ye);
         auto body = [&](auto check_tag) {
             constexpr bool CHECK = decltype(check_tag)::value;
+            const uint8_t *vit = vrow;                         // first row of the iteration
+            uint8_t *op = ocol + (long long)ylo6<N, D>(G::S0) * opitch;   // next output row (rows come out in order)
+            int yit = ybase;
+            // centre rows of phase-0 outputs lie A rows back; for the first A rows of a chunk that is the previous region
+            int wrapseq[G::U];
+#pragma unroll
+            for (int u = 0; u < G::U; u++) wrapseq[u] = wrapoff;
 #pragma unroll 1
             for (int it = 0; it < G::RB / G::U; it++) {
-                const uint8_t *vit = vrow + it * (G::U * SWM);
-                uint8_t *oit = ocol + (long long)(it * (N * G::U / D)) * opitch;
-                const int yit = ybase + it * (N * G::U / D);
+                uint32_t fl = 0;                               // flags of this iteration, bit = row - yit
 #pragma unroll
                 for (int u = 0; u < G::U; u++) {
                     const int s0 = (G::S0 + u) % D, tq = (G::S0 + u) / D;   // completing centre = D*(t + tq) + s0
@@ -519,25 +564,24 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
                     // this row r is a phase-0 centre iff (s0 + A) % D == 0; with b = bytes * 2^-24 (fp16 subnormals):
                     //   zpost(r-2) = 8*v[r-2] - 3*b[r]  and  zpre(r) = 8*v[r] - 3*b[r-2], both times 2^-12, both exact
                     //   (|.| <= 2040 < 2^11).  K = 3/8 >= plan.cpp's K_k: negative means "may flip".
+                    //   Only 8*v*2^-12 is kept per row: -3*b[r-2] = -0.375 * (8*b[r-2]).
                     if (FILTER && (s0 + A) % D == 0) {
                         const int zs = (ZD == 2) ? (u & 1) : 0;       // D = 1: slot of row r-2 = slot this row overwrites
                         const uint32_t kQ = 0x78007800u;              // 32768 = 8 * 2^12 (fp16x2)
                         const uint32_t kP = 0xF200F200u;              // -12288 = -3 * 2^12
+                        const uint32_t kR = 0xB600B600u;              // -0.375
                         const uint32_t hn[4] = {h0, h1, h2, h3};
                         uint32_t zpost = 0, zpre = 0;
 #pragma unroll
                         for (int i = 0; i < VB / 2; i++) {
                             const uint32_t An = hmul2_u(hn[i], kQ);
                             zpost |= hfma2_u(hn[i], kP, zA[zs][i]);
-                            zpre |= hfma2_u(za[zs][i], kP, An);
-                            za[zs][i] = hn[i];
+                            zpre |= hfma2_u(zA[zs][i], kR, An);
                             zA[zs][i] = An;
                         }
-                        // output rows of centre r-2 = c+A-2 and of centre r = c+A, relative to ybase (static)
-                        const int yy_post = N * (it * G::U + G::S0 + u + A - 2) / D;
-                        const int yy_pre = N * (it * G::U + G::S0 + u + A) / D;
-                        if (zpost & 0x80008000u) fixrows |= 1u << yy_post;
-                        if (zpre & 0x80008000u) fixrows |= 1u << yy_pre;
+                        // output rows of centre r-2 = c+A-2 and of centre r = c+A, relative to yit (static)
+                        if (zpost & 0x80008000u) fl |= 1u << (N * (G::S0 + u + A - 2) / D);
+                        if (zpre & 0x80008000u) fl |= 1u << (N * (G::S0 + u + A) / D);
                     }
                     // ---- rows that received their last tap ----
                     {
@@ -549,9 +593,8 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
                             uint2 qv;
                             bool doubt = false;
                             if (ph == 0) {
-                                const int back = u - A;                   // centre row relative to this iteration's first row
-                                const uint8_t *crow = vit + back * SWM;
-                                if (back < 0 && it * G::U + back < 0) crow += wrapoff;   // previous ring region
+                                // centre row relative to this iteration's first row: u - A
+                                const uint8_t *crow = vit + (u - A) * SWM + ((u - A < 0) ? wrapseq[u] : 0);
                                 qv = *reinterpret_cast<const uint2 *>(crow);
                             } else {
                                 qv.x = quantise4(res[q][0], res[q][1], res[q][2], res[q][3]);
@@ -563,10 +606,10 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
                                 }
                                 q++;
                             }
-                            const int y = yit + yoff;
-                            if (CHECK && (y < ys || y >= ye)) continue;
-                            if (MODE == 0 && doubt) fixrows |= 1u << (it * (N * G::U / D) + yoff);
-                            uint8_t *orow = oit + (long long)yoff * opitch;
+                            uint8_t *orow = op;
+                            op += opitch;
+                            if (CHECK && (yit + yoff < ys || yit + yoff >= ye)) continue;
+                            if (MODE == 0 && doubt) fl |= 1u << yoff;
                             if (ST64) {
                                 *reinterpret_cast<uint2 *>(orow) = qv;
                             } else {
@@ -576,6 +619,12 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
                         }
                     }
                 }
+                if (MODE == 0) fixrows |= fl << (it * (N * G::U / D));
+                vit += G::U * SWM;
+                yit += N * G::U / D;
+                // rows lr-A of the next iteration: one more iteration's worth of them lies inside this chunk
+#pragma unroll
+                for (int u = 0; u < G::U; u++) wrapseq[u] = (u + G::U * (it + 1) - A >= 0) ? 0 : wrapseq[u];
             }
         };
         if (interior) body(std::false_type{}); else body(std::true_type{});
@@ -624,8 +673,8 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
         }
         if (chunk < 0) continue;
         mbar_wait(hdone0 + 8 * (chunk & 1), (chunk >> 1) & 1);
-        // every thread has read TMA stage (chunk & 1): refill it with chunk + 2
-        if (tid == 0 && chunk + 2 < nchunks) issue(chunk + 2);
+        // every thread has read the TMA stage of this chunk: refill it with chunk + STAGES
+        if (tid == 0 && chunk + G::STAGES < nchunks) issue(chunk + G::STAGES);
         if (v_active) v_pass(chunk);
         mbar_arrive(vdone0 + 8 * (chunk & 1));
     }
