@@ -38,6 +38,10 @@
 #include "../../include/lanczos_b200.h"
 #include "fast_common.cuh"
 
+#ifndef LZB_W
+#define LZB_W 1          // independent warps (strips) per CTA
+#endif
+
 namespace lzb {
 
 namespace {
@@ -66,11 +70,10 @@ __host__ __device__ constexpr int cdiv6(int a, int b) { return (a + b - 1) / b; 
 __host__ __device__ constexpr int cmax6(int a, int b) { return a > b ? a : b; }
 __host__ __device__ constexpr int lcm2(int d) { return d % 2 == 0 ? d : 2 * d; }
 
-template <int C, int A, int N, int D, int PH, int NT>
+template <int C, int A, int N, int D, int PH, int W>
 struct Geo6 {
-    static constexpr int THREADS = NT;
+    static constexpr int THREADS = 32 * W;              // W independent warps per CTA, one strip each
     static constexpr int VB = 8;                        // byte-columns per V thread
-    static constexpr int SW_MAX = VB * NT;              // strip width in output bytes
     static constexpr int TAPS = 2 * A;
     static constexpr int IN_B = PH * D * C;             // input bytes owned by one H item
     static constexpr int OUT_B = PH * N * C;            // output bytes produced by one H item
@@ -84,10 +87,14 @@ struct Geo6 {
     static constexpr int MIS = (PAD_L - HALO_L) % 8;              // window start inside its first 8-byte unit
     static constexpr int WIN0 = PAD_L - HALO_L - MIS;             // first 8-byte unit (byte offset) of group 0
     static constexpr int NW2 = (MIS + WIN_B + 7) / 8;             // 8-byte loads per H item
-    static constexpr int MAX_GROUPS = SW_MAX / OUT_B;
-    static constexpr int BOX_B = 16 * cdiv6(cmax6(PAD_L + MAX_GROUPS * IN_B + HALO_R, WIN0 + (MAX_GROUPS - 1) * IN_B + 8 * NW2), 16);
+    static constexpr int MAX_GROUPS = 32 / (OUT_B / VB);            // H items per row of a warp's strip (5 for 48-byte items)
+    static constexpr int SW_MAX = MAX_GROUPS * OUT_B;             // strip width = ring pitch in bytes (240)
+    // a TMA box must start on a 16-byte boundary of the row: strips whose input starts 8 bytes off get a box
+    // that starts 8 bytes early (XSHIFT_MAX extra bytes per row)
+    static constexpr int XSHIFT_MAX = ((MAX_GROUPS * IN_B) % 16 != 0) ? 8 : 0;
+    static constexpr int BOX_B = 16 * cdiv6(XSHIFT_MAX + cmax6(PAD_L + MAX_GROUPS * IN_B + HALO_R, WIN0 + (MAX_GROUPS - 1) * IN_B + 8 * NW2), 16);
     static constexpr int RB = 6;                                  // input rows per chunk
-    static constexpr int REGIONS = 4;                             // ring regions of RB rows: H(c+1) may run while V(c) reads
+    static constexpr int REGIONS = 2;                             // ring regions of RB rows: V(c) reads region c and the tail of c-1
     static constexpr int RING = REGIONS * RB;                     // intermediate rows kept in smem
     static constexpr int STAGE_B = 128 * ((RB * BOX_B + 127) / 128);  // TMA destinations must be 128-byte aligned
     static constexpr int STAGES = 4;                              // TMA stages in flight (a stage is refilled 3 chunks ahead)
@@ -95,10 +102,9 @@ struct Geo6 {
     static constexpr int S0 = (((1 - 2 * A) % D) + D) % D;
     static constexpr int U = lcm2(D);                             // rows per V loop iteration (even: filter delay line parity)
     static constexpr int YROWS = N * RB / D;                      // output rows completed per chunk
-    static constexpr int HROUNDS = (RB * MAX_GROUPS + NT - 1) / NT;
     static_assert(IN_B % 8 == 0, "H item input must be 8-byte aligned");
     static_assert(OUT_B % 16 == 0, "H item output must be 16-byte aligned");
-    static_assert(SW_MAX % OUT_B == 0, "strip must hold a whole number of H items");
+    static_assert(OUT_B % VB == 0 && RB * MAX_GROUPS <= 32 && SW_MAX / VB <= 32, "one H item and one V column per lane");
     static_assert(RB % U == 0, "chunk must be a whole number of V loop iterations");
     static_assert(TAPS - 1 <= RB, "tap rows must not reach further back than one ring region");
     static_assert(BOX_B / 4 <= 256, "TMA box too wide");
@@ -127,17 +133,11 @@ template <int N, int D, int TAPS> __host__ __device__ constexpr int nslot6() {  
 }
 
 template <class G>
-struct __align__(128) Smem6 {
+struct __align__(128) Smem6 {             // one per warp
     uint8_t in[G::STAGES][G::STAGE_B];    // TMA destinations, row lr at lr * BOX_B
     uint8_t ring[G::RING][G::SW_MAX];     // H-pass results (uint8), row r lives in slot (r - rs) % RING
     unsigned long long full[G::STAGES];   // TMA stage filled
-    unsigned long long hdone[2];          // every thread finished the H pass of chunk c (index c & 1)
-    unsigned long long vdone[2];          // every thread finished the V pass of chunk c (index c & 1)
 };
-
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 
 // Four bytes from up to four source words, positions known at compile time after unrolling: one PRMT for
 // the first two distinct sources, one more per further source.
@@ -271,6 +271,7 @@ struct VFixArgs {
 template <int A, int N, int D, int KM, int RING, int SWM, int VB>
 __device__ __noinline__ int v_fix(const V6Params &p, const VFixArgs a) {
     constexpr int TAPS = 2 * A;
+    static_assert(VB == 8, "v_fix re-checks one 8-byte column");
     int n_strict = 0;
 #pragma unroll 1
     for (uint32_t m = a.rows; m; m &= m - 1) {
@@ -279,20 +280,41 @@ __device__ __noinline__ int v_fix(const V6Params &p, const VFixArgs a) {
         const int ph = (y * D) % N;
         const int s0 = ((y * D) / N - A + 1 - a.rs) % RING;       // ring slot of the first tap row (full_TB.h:72)
         uint8_t *orow = a.ocol + (long long)yy * a.opitch;
+        uint32_t need = 0;                                        // bit e: byte e must be evaluated exactly
+        if (ph != 0) {
+            // the hot path's fp32 chains again for all 8 bytes (ascending taps, same weights: same bits)
+            float acc[VB];
+#pragma unroll
+            for (int i = 0; i < VB; i++) acc[i] = -p.guard_v;
+#pragma unroll
+            for (int k = 0; k < TAPS; k++) {
+                const uint2 w = *reinterpret_cast<const uint2 *>(a.col + ((s0 + k) % RING) * SWM);
+                float x[VB];
+                word_to_f32x4(w.x, x[0], x[1], x[2], x[3]);
+                word_to_f32x4(w.y, x[4], x[5], x[6], x[7]);
+                const float wk = p.wtab[ph * 8 + k];
+#pragma unroll
+                for (int i = 0; i < VB; i++) acc[i] = fmaf(x[i], wk, acc[i]);
+            }
+            const float g2 = 2.f * p.guard_v;
+            const uint32_t dx = quantise4(acc[0], acc[1], acc[2], acc[3]) ^ quantise4(acc[0] + g2, acc[1] + g2, acc[2] + g2, acc[3] + g2);
+            const uint32_t dy = quantise4(acc[4], acc[5], acc[6], acc[7]) ^ quantise4(acc[4] + g2, acc[5] + g2, acc[6] + g2, acc[7] + g2);
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                if ((dx >> (8 * e)) & 0xffu) need |= 1u << e;
+                if ((dy >> (8 * e)) & 0xffu) need |= 1u << (4 + e);
+            }
+        } else {
+            need = 0xffu;
+        }
+        need &= (a.nbytes >= VB) ? 0xffu : ((1u << a.nbytes) - 1u);
 #pragma unroll 1
-        for (int e = 0; e < VB; e++) {
-            if (e >= a.nbytes) break;
+        for (; need; need &= need - 1) {
+            const int e = __ffs(need) - 1;
             uint8_t taps_b[TAPS];
 #pragma unroll
             for (int k = 0; k < TAPS; k++) taps_b[k] = a.col[((s0 + k) % RING) * SWM + e];
-            if (ph == 0) {
-                if (phase0_safe<TAPS, KM>(taps_b, 1, p.align_ki)) continue;
-            } else {
-                float acc = -p.guard_v;      // the hot path's fp32 chain again (ascending taps: same bits)
-#pragma unroll
-                for (int k = 0; k < TAPS; k++) acc = fmaf((float)taps_b[k] * (1.f / 16777216.f), p.wtab[ph * 8 + k], acc);
-                if (quantise_f32(acc) == quantise_f32(acc + 2.f * p.guard_v)) continue;
-            }
+            if (ph == 0 && phase0_safe<TAPS, KM>(taps_b, 1, p.align_ki)) continue;
             if (p.uniform_y && N <= 8) orow[e] = exact_taps<TAPS>(taps_b, 1, [&](int k) { return p.wdtab[ph * 8 + k]; });
             else orow[e] = exact_taps<TAPS>(taps_b, 1, [&](int k) { return p.wdy[(long long)y * TAPS + k]; });
             n_strict++;
@@ -301,10 +323,10 @@ __device__ __noinline__ int v_fix(const V6Params &p, const VFixArgs a) {
     return n_strict;
 }
 
-template <int C, int A, int N, int D, int PH, int KM, int NT, int MODE, bool ST64>
-__global__ void __launch_bounds__(NT, (NT == 96 ? 5 : 4))
+template <int C, int A, int N, int D, int PH, int KM, int W, int MODE, bool ST64>
+__global__ void __launch_bounds__(32 * W, 16 / W)
 lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ V6Params p) {
-    using G = Geo6<C, A, N, D, PH, NT>;
+    using G = Geo6<C, A, N, D, PH, W>;
     constexpr int TAPS = G::TAPS;
     constexpr int SWM = G::SW_MAX;
     constexpr int VB = G::VB;
@@ -314,10 +336,12 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
     constexpr bool FILTER = (MODE == 0) && (KM != 0);
     static_assert(KM == 0 || (A == 3 && KM == 0x11), "phase-0 row filter is written for the +-2 residues of a = 3");
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    Smem6<G> &sm = *reinterpret_cast<Smem6<G> *>(smem_raw);
-
-    const int tid = threadIdx.x;
-    const int strip = blockIdx.x, seg = blockIdx.y, frame = blockIdx.z;
+    // every warp works on its own strip with its own TMA stages, ring and barriers: nothing is shared between
+    // the warps of a CTA, so there is no CTA-wide synchronisation anywhere
+    const int tid = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Smem6<G> &sm = reinterpret_cast<Smem6<G> *>(smem_raw)[warp];
+    const int strip = blockIdx.x * W + warp, seg = blockIdx.y, frame = blockIdx.z;
+    if (strip * p.sw >= p.out_w * C) return;
     uint8_t *out_frame = p.out + (long long)frame * p.out_frame_stride;
 
     // horizontal extent
@@ -326,6 +350,7 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
     const int valid_bytes = min(p.sw, row_bytes - obyte0);    // > 0 by construction of the grid
     const int groups = min(p.groups, (valid_bytes + G::OUT_B - 1) / G::OUT_B);
     const int ibyte0 = (obyte0 / (N * C)) * (D * C);          // first input byte column of the strip
+    const int xshift = (ibyte0 - G::PAD_L) & 15;              // 0 or 8: the TMA box starts that many bytes early
     // vertical extent: periods [pv0, pv1) -> output rows [N*pv0, N*pv1), clipped to the band
     const int pv0 = p.vperiod0 + seg * p.seg_periods;
     const int y_end_band = p.out_row0 + p.out_rows;
@@ -336,24 +361,20 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
     const int nrows = D * (pv1 - pv0) + TAPS - 1;             // rows to push
     const int nchunks = (nrows + G::RB - 1) / G::RB;
 
-    uint32_t full0 = smem_u32(&sm.full[0]), hdone0 = smem_u32(&sm.hdone[0]), vdone0 = smem_u32(&sm.vdone[0]);
-    // keep the addresses in registers: without this they are re-derived from the CTA's shared window at every use
-    asm volatile("" : "+r"(full0), "+r"(hdone0), "+r"(vdone0));
+    uint32_t full0 = smem_u32(&sm.full[0]);
+    // keep the address in a register: without this it is re-derived from the CTA's shared window at every use
+    asm volatile("" : "+r"(full0));
     if (tid == 0) {
         for (int i = 0; i < G::STAGES; i++) mbar_init(full0 + 8 * i, 1);
-        mbar_init(hdone0, NT);
-        mbar_init(hdone0 + 8, NT);
-        mbar_init(vdone0, NT);
-        mbar_init(vdone0 + 8, NT);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
+    __syncwarp();
 
     constexpr uint32_t kStageBytes = G::RB * G::BOX_B;
     auto issue = [&](int chunk) {
         const uint32_t bar = full0 + 8 * (chunk % G::STAGES);
         mbar_expect_tx(bar, kStageBytes);
-        tma_load_3d(smem_u32(&sm.in[chunk % G::STAGES][0]), &in_map, (ibyte0 - G::PAD_L) / 4, rs + chunk * G::RB - p.in_row0, frame, bar);
+        tma_load_3d(smem_u32(&sm.in[chunk % G::STAGES][0]), &in_map, (ibyte0 - G::PAD_L - xshift) / 4, rs + chunk * G::RB - p.in_row0, frame, bar);
     };
     if (tid == 0) {
         for (int i = 0; i < G::STAGES && i < nchunks; i++) issue(i);
@@ -362,11 +383,11 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
     // ------------------------------ H pass of one chunk ------------------------------
     int n_strict = 0;
     const float guard_h = p.guard_h, g2h = 2.f * p.guard_h;
-    // item = round * NT + tid -> (row, group); the first round's mapping is the same for every chunk
+    // lane -> (row, group) of its H item; the mapping is the same for every chunk
     int h_src0, h_dst0;
     {
         const int lr = tid / groups, g = tid - lr * groups;
-        h_src0 = lr * G::BOX_B + G::WIN0 + g * G::IN_B;
+        h_src0 = lr * G::BOX_B + xshift + G::WIN0 + g * G::IN_B;
         h_dst0 = lr * SWM + g * G::OUT_B;
         asm volatile("" : "+r"(h_src0), "+r"(h_dst0));
     }
@@ -374,16 +395,9 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
         const int st = chunk % G::STAGES;
         mbar_wait(full0 + 8 * st, (chunk / G::STAGES) & 1);
         const int slot0 = (chunk % G::REGIONS) * G::RB;          // ring slot of this chunk's first row
-#pragma unroll 1
-        for (int hr = 0; hr < G::HROUNDS; hr++) {
-            const int item = hr * NT + tid;
-            if (item >= G::RB * groups) break;
-            int src_off = h_src0, dst_off = h_dst0;
-            if (hr > 0) {
-                const int lr = item / groups, g = item - lr * groups;
-                src_off = lr * G::BOX_B + G::WIN0 + g * G::IN_B;
-                dst_off = lr * SWM + g * G::OUT_B;
-            }
+        if (tid < G::RB * groups) {
+            const int item = tid;
+            const int src_off = h_src0, dst_off = h_dst0;
             const uint2 *src = reinterpret_cast<const uint2 *>(&sm.in[st][src_off]);
             // srcw[0 .. 2*NW2): raw input words; srcw[2*NW2 ..): quantised interpolated samples, 4 per word
             uint32_t srcw[2 * G::NW2 + G::ND];
@@ -476,13 +490,12 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
             if (fix_g != 0 || (int)zor < 0) {
                 HFixArgs a;
                 const int lr = item / groups, g = item - lr * groups;
-                a.in_row = &sm.in[st][lr * G::BOX_B]; a.ring_row = drow; a.gbyte0 = g * G::OUT_B;
+                a.in_row = &sm.in[st][lr * G::BOX_B + xshift]; a.ring_row = drow; a.gbyte0 = g * G::OUT_B;
                 a.obyte0 = obyte0; a.ibyte0 = ibyte0; a.valid_bytes = valid_bytes;
                 a.fix_g = fix_g; a.fix_z = zor >> 31; a.guard = guard_h;
                 n_strict += h_fix<C, A, N, D, PH, KM, G::PAD_L>(p, a);
             }
         }
-        mbar_arrive(hdone0 + 8 * (chunk & 1));
     };
 
     // ------------------------------ V-pass state ------------------------------
@@ -663,20 +676,13 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
     };
 
     // ------------------------------ pipeline ------------------------------
-    // iteration c: H(c+1) [needs V(c-2) finished by everyone: ring region (c+1) % 4 is free], then V(c)
-    // [needs H(c) finished by everyone].  Both conditions were signalled one phase earlier, so the waits are
-    // normally already satisfied: no CTA-wide barrier in the loop.
-    for (int chunk = -1; chunk < nchunks; chunk++) {
-        if (chunk + 1 < nchunks) {
-            if (chunk >= 2) mbar_wait(vdone0 + 8 * (chunk & 1), ((chunk - 2) >> 1) & 1);
-            h_pass(chunk + 1);
-        }
-        if (chunk < 0) continue;
-        mbar_wait(hdone0 + 8 * (chunk & 1), (chunk >> 1) & 1);
-        // every thread has read the TMA stage of this chunk: refill it with chunk + STAGES
+    for (int chunk = 0; chunk < nchunks; chunk++) {
+        h_pass(chunk);
+        __syncwarp();
+        // every lane has read the TMA stage of this chunk: refill it with chunk + STAGES
         if (tid == 0 && chunk + G::STAGES < nchunks) issue(chunk + G::STAGES);
         if (v_active) v_pass(chunk);
-        mbar_arrive(vdone0 + 8 * (chunk & 1));
+        __syncwarp();
     }
     if (p.strict_counter && n_strict) atomicAdd(p.strict_counter, (unsigned long long)n_strict);
 }
@@ -684,24 +690,14 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int C, int A, int N, int D, int PH, int KM, int NT, int MODE, bool ST64>
+template <int C, int A, int N, int D, int PH, int KM, int W, int MODE, bool ST64>
 int launch_v6_one(const KParams &k, const FastHostTables &t, cudaStream_t s) {
-    using G = Geo6<C, A, N, D, PH, NT>;
+    using G = Geo6<C, A, N, D, PH, W>;
     EncodeFn encode = get_encode();
     if (!encode) return -1;
     const int row_bytes = k.out_w * C;
-    // strip width: a multiple of OUT_B (<= 8*NT bytes) whose input start stays 16-byte aligned for every
-    // strip (TMA needs a 16-byte aligned box start), wasting the fewest threads
-    int best_groups = 0;
-    double best_eff = -1;
-    for (int gr = G::MAX_GROUPS; gr >= 1; gr--) {
-        if ((gr * G::IN_B) % 16 != 0) continue;
-        const int sw_c = gr * G::OUT_B;
-        const int strips_c = (row_bytes + sw_c - 1) / sw_c;
-        const double eff = (double)row_bytes / ((double)strips_c * G::SW_MAX);
-        if (eff > best_eff + 1e-9) { best_eff = eff; best_groups = gr; }
-    }
-    if (best_groups == 0) return -1;
+    // one strip per warp: MAX_GROUPS H items wide (fewer if the image is narrower than that)
+    const int best_groups = std::min(G::MAX_GROUPS, (row_bytes + G::OUT_B - 1) / G::OUT_B);
     const int sw = best_groups * G::OUT_B;
     const int strips = (row_bytes + sw - 1) / sw;
     const int vperiod0 = k.out_row0 / N;
@@ -711,18 +707,18 @@ int launch_v6_one(const KParams &k, const FastHostTables &t, cudaStream_t s) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    auto kern = lanczos_v6_kernel<C, A, N, D, PH, KM, NT, MODE, ST64>;
-    const size_t smem = sizeof(Smem6<G>) + 128;
+    auto kern = lanczos_v6_kernel<C, A, N, D, PH, KM, W, MODE, ST64>;
+    const size_t smem = W * sizeof(Smem6<G>) + 128;
     static bool attr_set[64] = {};
     static int ctas_per_sm[64] = {};
     if (!attr_set[dev & 63]) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NT, smem) != cudaSuccess || nb < 1) nb = 4;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32 * W, smem) != cudaSuccess || nb < 1) nb = 4;
         ctas_per_sm[dev & 63] = nb;
         attr_set[dev & 63] = true;
     }
-    const long long slots = (long long)ctas_per_sm[dev & 63] * sms;
+    const long long slots = (long long)ctas_per_sm[dev & 63] * sms * W;      // resident warps = strips in flight
     const long long cols = (long long)strips * k.n_frames;
     const int max_segs = std::max(1, vperiods / std::max(1, (2 * G::RB) / D));
     int segs = 1;
@@ -770,8 +766,8 @@ int launch_v6_one(const KParams &k, const FastHostTables &t, cudaStream_t s) {
         for (int q = 0; q < 8; q++) p.wdtab[ph * 8 + q] = q < 2 * A ? t.phase_wd[ph * 2 * A + q] : 0.0;
     p.strict_counter = k.strict_counter;
 
-    dim3 grid(strips, segs, k.n_frames);
-    kern<<<grid, NT, smem, s>>>(map, p);
+    dim3 grid((strips + W - 1) / W, segs, k.n_frames);
+    kern<<<grid, 32 * W, smem, s>>>(map, p);
     return (int)cudaGetLastError();
 }
 
@@ -799,10 +795,10 @@ int launch_v6(const KParams &k, const FastHostTables &t, int *kernel_id, cudaStr
 #define LZ6_CASE(c, a, n, d, ph, kmask, id)                                                            \
     if (C == c && A == a && N == n && D == d && km == (kmask)) {                                        \
         *kernel_id = id;                                                                                \
-        if (mode == 0) return st64 ? launch_v6_one<c, a, n, d, ph, kmask, 96, 0, true>(k, t, s)         \
-                                   : launch_v6_one<c, a, n, d, ph, kmask, 96, 0, false>(k, t, s);       \
-        return st64 ? launch_v6_one<c, a, n, d, ph, kmask, 96, 1, true>(k, t, s)                        \
-                    : launch_v6_one<c, a, n, d, ph, kmask, 96, 1, false>(k, t, s);                      \
+        if (mode == 0) return st64 ? launch_v6_one<c, a, n, d, ph, kmask, LZB_W, 0, true>(k, t, s)         \
+                                   : launch_v6_one<c, a, n, d, ph, kmask, LZB_W, 0, false>(k, t, s);       \
+        return st64 ? launch_v6_one<c, a, n, d, ph, kmask, LZB_W, 1, true>(k, t, s)                        \
+                    : launch_v6_one<c, a, n, d, ph, kmask, LZB_W, 1, false>(k, t, s);                      \
     }
     // a = 3: sin(2*pi) < 0 in double, so the |d| = 2 taps (k = 0 and k = 4) carry negative residues
     LZ6_CASE(3, 3, 2, 1, 8, 0x11, 1)
