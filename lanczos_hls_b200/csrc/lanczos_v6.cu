@@ -38,6 +38,9 @@
 #include "../../include/lanczos_b200.h"
 #include "fast_common.cuh"
 
+#ifndef LZB_V_FFMA2
+#define LZB_V_FFMA2 1   // V-pass multiply-adds as FFMA2 over column pairs
+#endif
 #ifndef LZB_W
 #define LZB_W 1          // independent warps (strips) per CTA
 #endif
@@ -562,6 +565,18 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
                             for (int yr = ylo6<N, D>(sdc); yr < yhi6<N, D>(sdc); yr++) {
                                 const int ph = (yr * D) % N;
                                 if (ph == 0) continue;
+#if LZB_V_FFMA2
+                                // two columns per FFMA2 (one issue slot for two FMAs; same rounding as two FFMAs)
+                                const float2 wk2 = make_float2(p.wtab[ph * 8 + k], p.wtab[ph * 8 + k]);
+#pragma unroll
+                                for (int i = 0; i < VB; i += 2) {
+                                    const float2 x2 = make_float2(x[i], x[i + 1]);
+                                    const float2 a2 = (dc < TAPS - 1) ? make_float2(acc[q][i], acc[q][i + 1]) : make_float2(-guard_v, -guard_v);
+                                    const float2 r2 = __ffma2_rn(x2, wk2, a2);
+                                    if (dc == 0) { res[q][i] = r2.x; res[q][i + 1] = r2.y; }
+                                    else { acc[q - cnt0][i] = r2.x; acc[q - cnt0][i + 1] = r2.y; }
+                                }
+#else
 #pragma unroll
                                 for (int i = 0; i < VB; i++) {
                                     const float wk = p.wtab[ph * 8 + k];
@@ -569,6 +584,7 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
                                     else if (dc < TAPS - 1) acc[q - cnt0][i] = fmaf(x[i], wk, acc[q][i]);
                                     else acc[q - cnt0][i] = fmaf(x[i], wk, -guard_v);
                                 }
+#endif
                                 q++;
                             }
                         }
