@@ -198,14 +198,14 @@ int run_device(const DevicePlan &dp, unsigned flags, const uint8_t *d_in, uint8_
     if (g_stats_enabled) CU(cudaMemsetAsync(dp.strict_counter, 0, 8, s));
     if (n_frames <= 0 || out_rows <= 0) return LANCZOS_OK;
 
-    int kid = 0;
+    int kid = 0, alias_done = 0;
     int frc = -1;
     if (!(flags & LANCZOS_FLAG_GENERIC_KERNEL)) {
         FastHostTables t{h.phase_w.data(), h.phase_wd.data(), h.align_k.data(), h.x.aligned_exact ? 1 : 0,
                          h.y.aligned_exact ? 1 : 0, h.x.uniform_phase ? 1 : 0, h.y.uniform_phase ? 1 : 0};
         // development switch: LZB_IMPL=v5 selects the first-generation specialised kernels
         const char *impl = getenv("LZB_IMPL");
-        if (!(impl && impl[0] == 'v' && impl[1] == '5')) frc = launch_v6(p, t, &kid, s);
+        if (!(impl && impl[0] == 'v' && impl[1] == '5')) frc = launch_v6(p, t, &kid, &alias_done, s);
         if (frc < 0 && !(flags & LANCZOS_FLAG_TOLERANCE_1LSB)) frc = launch_fast(p, t, &kid, s);
     }
     if (frc > 0) return cuda_fail((cudaError_t)frc, "launch_fast");
@@ -217,7 +217,9 @@ int run_device(const DevicePlan &dp, unsigned flags, const uint8_t *d_in, uint8_
     if (e != cudaSuccess) return cuda_fail(e, "launch_generic");
     g_stats.kernel_launches++;
     g_stats.kernel_id = kid;
-    if (h.alias_rows > 0 && out_row0 < h.alias_rows) {
+    if (h.alias_rows > 0 && out_row0 < h.alias_rows && alias_done) {
+        g_stats.alias_rows = std::min(h.alias_rows, out_row0 + out_rows) - out_row0;
+    } else if (h.alias_rows > 0 && out_row0 < h.alias_rows) {
         e = (cudaError_t)launch_alias_rows(p, s);
         if (e != cudaSuccess) return cuda_fail(e, "launch_alias_rows");
         g_stats.kernel_launches++;

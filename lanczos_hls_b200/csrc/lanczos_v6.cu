@@ -62,6 +62,7 @@ struct V6Params {
     float guard_h, guard_v;   // rigorous fp32 error bounds (x1.05) of the two summation orders
     int uniform_x, uniform_y; // double weights identical for all coordinates of a phase -> wdtab usable
     int strict_v_identity;    // 0 with LANCZOS_FLAG_FAST_ALIGNED
+    int alias_rows, alias_top_row;   // in-place top rows done inside this kernel (0 = none / separate kernel)
     float align_k[8];         // phase-0 "cannot flip" constants
     int align_ki[8];          // the same, ceil(K * 2^16), for the integer re-check in the slow paths
     float wtab[32 * 8];       // polyphase table [N][8] (padded to 8 taps), N <= 32, times 2^24
@@ -324,6 +325,62 @@ __device__ __noinline__ int v_fix(const V6Params &p, const VFixArgs a) {
         }
     }
     return n_strict;
+}
+
+// The reference's column pass runs in place from the bottom row up (full_TB.h:67-77): output row yy reads rows
+// first..last of the same plane, and every row i > yy of that window already holds its FINAL value.  Only the
+// first alias_rows rows are affected.  After chunk 1 the ring still holds the (bit-exact) horizontal results of
+// rows 0..2*RB-A, so the warp that owns the strip replays the recurrence for its columns in double arithmetic.
+struct AliasArgs {
+    const uint8_t *col;       // this thread's column in ring row 0 (slot of intermediate row rs)
+    uint8_t *ocol;            // this thread's column in output row 0
+    long long opitch;
+    int rs, nbytes;
+};
+
+template <int A, int N, int D, int RB, int SWM, int VB>
+__device__ __noinline__ void alias_fix(const V6Params &p, const AliasArgs a) {
+    constexpr int TAPS = 2 * A;
+    constexpr int TOP = 2 * RB - A;                 // last intermediate row in the ring after chunk 1 (first one: -(A-1))
+    static_assert(VB == 8 && TOP - 1 < 16, "alias_fix handles one 8-byte column, rows 0..15");
+    // the segment starts at output row 0, so intermediate row i sits in ring slot i + A - 1 (rs = -(A-1)).
+    // Rows outside the image hold zeros (TMA fill), which add +-0 to the sum exactly like the reference's
+    // clipped window (full_TB.h:72).
+    uint2 fin[TOP + 1];                             // final values of rows already replaced
+#pragma unroll
+    for (int i = 0; i <= TOP; i++) fin[i] = make_uint2(0u, 0u);
+#pragma unroll
+    for (int yy = TOP - 1; yy >= 0; yy--) {
+        if (yy > p.alias_top_row) continue;
+        const int first = (yy * D) / N - A + 1;
+        const int ph = (yy * D) % N;
+        double sum[VB];
+#pragma unroll
+        for (int e = 0; e < VB; e++) sum[e] = 0.0;
+#pragma unroll
+        for (int k = 0; k < TAPS; k++) {
+            const int i = first + k;
+            if (i > TOP) continue;                  // cannot happen for rows the host lets this path handle
+            const uint2 v = (i > yy) ? fin[i] : *reinterpret_cast<const uint2 *>(a.col + (i + A - 1) * SWM);
+            const double w = (p.uniform_y && N <= 8) ? p.wdtab[ph * 8 + k] : p.wdy[(long long)yy * TAPS + k];
+#pragma unroll
+            for (int e = 0; e < VB; e++) {
+                const uint32_t word = e < 4 ? v.x : v.y;
+                const double vd = __hiloint2double(0x43300000, (int)((word >> (8 * (e & 3))) & 0xffu)) - 4503599627370496.0;
+                sum[e] = __dadd_rn(sum[e], __dmul_rn(vd, w));
+            }
+        }
+        uint32_t q[VB];
+#pragma unroll
+        for (int e = 0; e < VB; e++) q[e] = quantise_f64(sum[e]);
+        fin[yy] = make_uint2(q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24), q[4] | (q[5] << 8) | (q[6] << 16) | (q[7] << 24));
+        if (yy < p.alias_rows) {
+            uint8_t *orow = a.ocol + (long long)yy * a.opitch;
+#pragma unroll
+            for (int e = 0; e < VB; e++)
+                if (e < a.nbytes) orow[e] = (uint8_t)q[e];
+        }
+    }
 }
 
 template <int C, int A, int N, int D, int PH, int KM, int W, int MODE, bool ST64>
@@ -698,6 +755,13 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
         // every lane has read the TMA stage of this chunk: refill it with chunk + STAGES
         if (tid == 0 && chunk + G::STAGES < nchunks) issue(chunk + G::STAGES);
         if (v_active) v_pass(chunk);
+        // in-place top rows of the reference: replayed exactly once rows 0..alias_top_row+A are in the ring
+        if (p.alias_rows > 0 && ys == 0 && v_active && chunk == (nchunks > 1 ? 1 : 0)) {
+            AliasArgs a;
+            a.col = vcol; a.ocol = out_frame + obyte0 + VB * tid; a.opitch = opitch; a.rs = rs;
+            a.nbytes = min(VB, valid_bytes - VB * tid);
+            alias_fix<A, N, D, G::RB, SWM, VB>(p, a);
+        }
         __syncwarp();
     }
     if (p.strict_counter && n_strict) atomicAdd(p.strict_counter, (unsigned long long)n_strict);
@@ -707,7 +771,7 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
 // host side
 // ---------------------------------------------------------------------------------------------
 template <int C, int A, int N, int D, int PH, int KM, int W, int MODE, bool ST64>
-int launch_v6_one(const KParams &k, const FastHostTables &t, cudaStream_t s) {
+int launch_v6_one(const KParams &k, const FastHostTables &t, int *alias_in_kernel, cudaStream_t s) {
     using G = Geo6<C, A, N, D, PH, W>;
     EncodeFn encode = get_encode();
     if (!encode) return -1;
@@ -774,6 +838,15 @@ int launch_v6_one(const KParams &k, const FastHostTables &t, cudaStream_t s) {
     p.guard_h = k.guard_outer; p.guard_v = k.guard_asc;
     p.uniform_x = t.uniform_x; p.uniform_y = t.uniform_y;
     p.strict_v_identity = (k.flags & LANCZOS_FLAG_FAST_ALIGNED) ? 0 : 1;
+    // in-place top rows inside the kernel: the band must start at row 0 with input row 0 present, and every
+    // intermediate row the recurrence touches must still be in the ring after chunk 1 (rows -(a-1) .. 2*RB-a)
+    *alias_in_kernel = 0;
+    if (k.alias_rows > 0 && k.out_row0 == 0 && k.in_row0 == 0 && k.alias_in_rows <= 2 * G::RB - A + 1 && k.alias_top_row <= 2 * G::RB - A - 1 &&
+        k.alias_rows <= k.out_rows) {
+        p.alias_rows = k.alias_rows;
+        p.alias_top_row = k.alias_top_row;
+        *alias_in_kernel = 1;
+    }
     for (int i = 0; i < 8; i++) p.align_k[i] = i < 2 * A ? t.align_k[i] : 0.f;
     for (int i = 0; i < 8; i++) p.align_ki[i] = (int)std::ceil((double)p.align_k[i] * 65536.0 * 1.0001);
     for (int ph = 0; ph < N; ph++)
@@ -790,7 +863,7 @@ int launch_v6_one(const KParams &k, const FastHostTables &t, cudaStream_t s) {
 }  // namespace
 
 // Returns 0 on launch, >0 cudaError, -1 when no specialised kernel applies (caller falls back).
-int launch_v6(const KParams &k, const FastHostTables &t, int *kernel_id, cudaStream_t s) {
+int launch_v6(const KParams &k, const FastHostTables &t, int *kernel_id, int *alias_in_kernel, cudaStream_t s) {
     // layout requirements of the TMA map and of the 32-bit/64-bit/128-bit accesses
     if ((k.in_w * k.channels) % 4 != 0 || (k.out_w * k.channels) % 4 != 0) return -1;
     if (k.in_pitch % 16 != 0 || k.out_pitch % 4 != 0) return -1;
@@ -811,10 +884,10 @@ int launch_v6(const KParams &k, const FastHostTables &t, int *kernel_id, cudaStr
 #define LZ6_CASE(c, a, n, d, ph, kmask, id)                                                            \
     if (C == c && A == a && N == n && D == d && km == (kmask)) {                                        \
         *kernel_id = id;                                                                                \
-        if (mode == 0) return st64 ? launch_v6_one<c, a, n, d, ph, kmask, LZB_W, 0, true>(k, t, s)         \
-                                   : launch_v6_one<c, a, n, d, ph, kmask, LZB_W, 0, false>(k, t, s);       \
-        return st64 ? launch_v6_one<c, a, n, d, ph, kmask, LZB_W, 1, true>(k, t, s)                        \
-                    : launch_v6_one<c, a, n, d, ph, kmask, LZB_W, 1, false>(k, t, s);                      \
+        if (mode == 0) return st64 ? launch_v6_one<c, a, n, d, ph, kmask, LZB_W, 0, true>(k, t, alias_in_kernel, s)         \
+                                   : launch_v6_one<c, a, n, d, ph, kmask, LZB_W, 0, false>(k, t, alias_in_kernel, s);       \
+        return st64 ? launch_v6_one<c, a, n, d, ph, kmask, LZB_W, 1, true>(k, t, alias_in_kernel, s)                        \
+                    : launch_v6_one<c, a, n, d, ph, kmask, LZB_W, 1, false>(k, t, alias_in_kernel, s);                      \
     }
     // a = 3: sin(2*pi) < 0 in double, so the |d| = 2 taps (k = 0 and k = 4) carry negative residues
     LZ6_CASE(3, 3, 2, 1, 8, 0x11, 1)
