@@ -41,6 +41,9 @@
 #ifndef LZB_V_FFMA2
 #define LZB_V_FFMA2 1   // V-pass multiply-adds as FFMA2 over column pairs
 #endif
+#ifndef LZB_MINB
+#define LZB_MINB 16      // resident warps per SM the register allocation aims for
+#endif
 #ifndef LZB_W
 #define LZB_W 1          // independent warps (strips) per CTA
 #endif
@@ -384,7 +387,7 @@ __device__ __noinline__ void alias_fix(const V6Params &p, const AliasArgs a) {
 }
 
 template <int C, int A, int N, int D, int PH, int KM, int W, int MODE, bool ST64>
-__global__ void __launch_bounds__(32 * W, 16 / W)
+__global__ void __launch_bounds__(32 * W, LZB_MINB / W)
 lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ V6Params p) {
     using G = Geo6<C, A, N, D, PH, W>;
     constexpr int TAPS = G::TAPS;
@@ -461,6 +464,8 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
             const uint2 *src = reinterpret_cast<const uint2 *>(&sm.in[st][src_off]);
             // srcw[0 .. 2*NW2): raw input words; srcw[2*NW2 ..): quantised interpolated samples, 4 per word
             uint32_t srcw[2 * G::NW2 + G::ND];
+            uint32_t fix_g = 0;        // bit per packed word of interpolated samples: truncation in doubt
+            uint32_t zor = 0;          // sign bit: some phase-0 sample may flip
             float f[G::NW2 * 8];
 #pragma unroll
             for (int wi = 0; wi < G::NW2; wi++) {
@@ -471,7 +476,6 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
                 word_to_f32x4(w.y, f[8 * wi + 4], f[8 * wi + 5], f[8 * wi + 6], f[8 * wi + 7]);
             }
             // window byte k (k = 0 is HALO_L bytes left of the item's own input) = f[MIS + k] * 2^24
-            uint32_t fix_g = 0;        // bit per packed word of interpolated samples: truncation in doubt
             // interpolated samples, in output order, packed 4 per word
 #pragma unroll
             for (int dw = 0; dw < G::ND; dw++) {
@@ -503,7 +507,6 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
             }
             // phase-0 samples are copies of the centre tap; "cannot flip" filter of plan.cpp:
             // v - sum K_k*b_k >= 0 over the negative residues -> the reference returns v as well
-            uint32_t zor = 0;
             if (KM != 0) {
 #pragma unroll
                 for (int per = 0; per < PH; per++)
@@ -686,8 +689,11 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
                                 qv.x = quantise4(res[q][0], res[q][1], res[q][2], res[q][3]);
                                 qv.y = quantise4(res[q][4], res[q][5], res[q][6], res[q][7]);
                                 if (MODE == 0) {
-                                    const uint32_t bx = quantise4(res[q][0] + g2v, res[q][1] + g2v, res[q][2] + g2v, res[q][3] + g2v);
-                                    const uint32_t by = quantise4(res[q][4] + g2v, res[q][5] + g2v, res[q][6] + g2v, res[q][7] + g2v);
+                                    const float2 gg = make_float2(g2v, g2v);
+                                    const float2 b01 = __fadd2_rn(make_float2(res[q][0], res[q][1]), gg), b23 = __fadd2_rn(make_float2(res[q][2], res[q][3]), gg);
+                                    const float2 b45 = __fadd2_rn(make_float2(res[q][4], res[q][5]), gg), b67 = __fadd2_rn(make_float2(res[q][6], res[q][7]), gg);
+                                    const uint32_t bx = quantise4(b01.x, b01.y, b23.x, b23.y);
+                                    const uint32_t by = quantise4(b45.x, b45.y, b67.x, b67.y);
                                     doubt = (qv.x != bx) || (qv.y != by);
                                 }
                                 q++;
