@@ -202,10 +202,11 @@ int run_device(const DevicePlan &dp, unsigned flags, const uint8_t *d_in, uint8_
     int frc = -1;
     if (!(flags & LANCZOS_FLAG_GENERIC_KERNEL)) {
         FastHostTables t{h.phase_w.data(), h.phase_wd.data(), h.align_k.data(), h.x.aligned_exact ? 1 : 0,
-                         h.y.aligned_exact ? 1 : 0, h.x.uniform_phase ? 1 : 0, h.y.uniform_phase ? 1 : 0};
+                         h.y.aligned_exact ? 1 : 0, h.x.uniform_phase ? 1 : 0, h.y.uniform_phase ? 1 : 0, h.x.i0.data()};
         // development switch: LZB_IMPL=v5 selects the first-generation specialised kernels
         const char *impl = getenv("LZB_IMPL");
         if (!(impl && impl[0] == 'v' && impl[1] == '5')) frc = launch_v6(p, t, &kid, &alias_done, s);
+        if (frc < 0 && !(impl && impl[0] == 'v' && impl[1] == '5')) frc = launch_dyn(p, t, &kid, s);
         if (frc < 0 && !(flags & LANCZOS_FLAG_TOLERANCE_1LSB)) frc = launch_fast(p, t, &kid, s);
     }
     if (frc > 0) return cuda_fail((cudaError_t)frc, "launch_fast");

@@ -38,11 +38,14 @@ struct FastHostTables {            // host-side views of the plan the specialise
     const float *align_k;          // [2a]
     int exact_x, exact_y;          // AxisTables.aligned_exact
     int uniform_x, uniform_y;      // AxisTables.uniform_phase
+    const int32_t *i0x_host;       // [out_w] host copy of AxisTables.i0 (x axis)
 };
 int launch_fast(const KParams &p, const FastHostTables &t, int *kernel_id, cudaStream_t s);
 // Second generation of the same (lanczos_v6.cu): 8-byte V columns, PRMT-spliced copies, scalar constant-bank FFMA.
 // *alias_in_kernel = 1 when the kernel also produced the in-place top rows (no launch_alias_rows needed).
 int launch_v6(const KParams &p, const FastHostTables &t, int *kernel_id, int *alias_in_kernel, cudaStream_t s);
+// Any-ratio member of the second generation (lanczos_dyn.cu): dynamic-phase H pass, static systolic V pass.
+int launch_dyn(const KParams &p, const FastHostTables &t, int *kernel_id, cudaStream_t s);
 // In-place top rows (full_TB.h:67-77 aliasing), exact double arithmetic.
 int launch_alias_rows(const KParams &p, cudaStream_t s);
 // Fixed-point HLS arithmetic (lanczos_hls.cu), integer scales; lut has a*n+1 entries in units of 2^-bp.
