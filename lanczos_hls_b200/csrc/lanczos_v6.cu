@@ -41,6 +41,9 @@
 #ifndef LZB_V_FFMA2
 #define LZB_V_FFMA2 1   // V-pass multiply-adds as FFMA2 over column pairs
 #endif
+#ifndef LZB_HROUNDS
+#define LZB_HROUNDS 2     // H rounds (of 32 / MAX_GROUPS rows) per chunk
+#endif
 #ifndef LZB_MINB
 #define LZB_MINB 16      // resident warps per SM the register allocation aims for
 #endif
@@ -100,23 +103,26 @@ struct Geo6 {
     // that starts 8 bytes early (XSHIFT_MAX extra bytes per row)
     static constexpr int XSHIFT_MAX = ((MAX_GROUPS * IN_B) % 16 != 0) ? 8 : 0;
     static constexpr int BOX_B = 16 * cdiv6(XSHIFT_MAX + cmax6(PAD_L + MAX_GROUPS * IN_B + HALO_R, WIN0 + (MAX_GROUPS - 1) * IN_B + 8 * NW2), 16);
-    static constexpr int RB = 6;                                  // input rows per chunk
+    static constexpr int HB = 32 / MAX_GROUPS;                    // rows one round of H items covers (one item per lane)
+    static constexpr int HROUNDS = LZB_HROUNDS;                   // H rounds per chunk
+    static constexpr int RB = HB * HROUNDS;                       // input rows per chunk
     static constexpr int REGIONS = 2;                             // ring regions of RB rows: V(c) reads region c and the tail of c-1
     static constexpr int RING = REGIONS * RB;                     // intermediate rows kept in smem
     static constexpr int STAGE_B = 128 * ((RB * BOX_B + 127) / 128);  // TMA destinations must be 128-byte aligned
-    static constexpr int STAGES = 4;                              // TMA stages in flight (a stage is refilled 3 chunks ahead)
+    static constexpr int STAGES = HROUNDS > 1 ? 3 : 4;            // TMA stages in flight
     // the first row pushed by a segment is rs = D*pv0 - A + 1, so (row - A) mod D is static per chunk row
     static constexpr int S0 = (((1 - 2 * A) % D) + D) % D;
     static constexpr int U = lcm2(D);                             // rows per V loop iteration (even: filter delay line parity)
     static constexpr int YROWS = N * RB / D;                      // output rows completed per chunk
     static_assert(IN_B % 8 == 0, "H item input must be 8-byte aligned");
     static_assert(OUT_B % 16 == 0, "H item output must be 16-byte aligned");
-    static_assert(OUT_B % VB == 0 && RB * MAX_GROUPS <= 32 && SW_MAX / VB <= 32, "one H item and one V column per lane");
+    static_assert(OUT_B % VB == 0 && HB * MAX_GROUPS <= 32 && SW_MAX / VB <= 32, "one H item per lane and round, one V column per lane");
     static_assert(RB % U == 0, "chunk must be a whole number of V loop iterations");
     static_assert(TAPS - 1 <= RB, "tap rows must not reach further back than one ring region");
     static_assert(BOX_B / 4 <= 256, "TMA box too wide");
     static_assert(N <= 32, "phase table too large for kernel params");
-    static_assert(YROWS + N * (S0 + A + 1) / D + 2 <= 32, "fix mask (bit per output row) too small");
+    static_assert(YROWS + N * (S0 + A + 1) / D + 2 <= 64, "fix mask (bit per output row) too small");
+    static_assert(cdiv6(S0 * N, D) + YROWS <= 32, "rows fixed per chunk must fit 32 bits");
     static_assert(ND <= 31, "H fix mask (bit per packed word) too small");
     static_assert(D <= 2, "phase-0 filter delay line assumes the +-2 rows are phase-0 centres themselves");
 };
@@ -344,7 +350,7 @@ struct AliasArgs {
 template <int A, int N, int D, int RB, int SWM, int VB>
 __device__ __noinline__ void alias_fix(const V6Params &p, const AliasArgs a) {
     constexpr int TAPS = 2 * A;
-    constexpr int TOP = 2 * RB - A;                 // last intermediate row in the ring after chunk 1 (first one: -(A-1))
+    constexpr int TOP = (2 * RB - A) < 12 ? (2 * RB - A) : 12;   // last intermediate row used (the ring holds -(A-1) .. 2*RB-A after chunk 1)
     static_assert(VB == 8 && TOP - 1 < 16, "alias_fix handles one 8-byte column, rows 0..15");
     // the segment starts at output row 0, so intermediate row i sits in ring slot i + A - 1 (rs = -(A-1)).
     // Rows outside the image hold zeros (TMA fill), which add +-0 to the sum exactly like the reference's
@@ -458,9 +464,11 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
         const int st = chunk % G::STAGES;
         mbar_wait(full0 + 8 * st, (chunk / G::STAGES) & 1);
         const int slot0 = (chunk % G::REGIONS) * G::RB;          // ring slot of this chunk's first row
-        if (tid < G::RB * groups) {
-            const int item = tid;
-            const int src_off = h_src0, dst_off = h_dst0;
+#pragma unroll 1
+        for (int hr = 0; hr < G::HROUNDS; hr++) {
+            if (tid >= G::HB * groups) break;
+            const int item = hr * G::HB * groups + tid;
+            const int src_off = h_src0 + hr * (G::HB * G::BOX_B), dst_off = h_dst0 + hr * (G::HB * SWM);
             const uint2 *src = reinterpret_cast<const uint2 *>(&sm.in[st][src_off]);
             // srcw[0 .. 2*NW2): raw input words; srcw[2*NW2 ..): quantised interpolated samples, 4 per word
             uint32_t srcw[2 * G::NW2 + G::ND];
@@ -583,7 +591,7 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
     const int t0_first = (rs - A - G::S0) / D;                 // exact division (also for negative values)
     int ybase = N * t0_first;                                  // output row of bit 0 of `fixrows` for the current chunk
     uint8_t *ocol = out_frame + obyte0 + VB * tid + (long long)(ybase - p.out_row0) * opitch;   // column in row ybase
-    uint32_t fixrows = 0;                                      // bit yy: look at output row ybase + yy again
+    unsigned long long fixrows = 0;                            // bit yy: look at output row ybase + yy again
 
     auto v_pass = [&](int chunk) {
         const int bslot = (chunk % G::REGIONS) * G::RB;
@@ -711,7 +719,7 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
                         }
                     }
                 }
-                if (MODE == 0) fixrows |= fl << (it * (N * G::U / D));
+                if (MODE == 0) fixrows |= (unsigned long long)fl << (it * (N * G::U / D));
                 vit += G::U * SWM;
                 yit += N * G::U / D;
                 // rows lr-A of the next iteration: one more iteration's worth of them lies inside this chunk
@@ -723,8 +731,8 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
         if (MODE == 0) {
             // rows [ylo(S0), ylo(S0) + YROWS) relative to ybase were stored in this chunk; later bits wait
             constexpr uint32_t kDone = (uint32_t)((1ull << (ylo6<N, D>(G::S0) + G::YROWS)) - 1ull);
-            uint32_t todo = fixrows & kDone;
-            fixrows = (fixrows & ~kDone) >> G::YROWS;
+            uint32_t todo = (uint32_t)fixrows & kDone;
+            fixrows = (fixrows & ~(unsigned long long)kDone) >> G::YROWS;
             if (!p.strict_v_identity) {      // LANCZOS_FLAG_FAST_ALIGNED: phase-0 rows stay plain copies
                 uint32_t ph0rows = 0;
 #pragma unroll
@@ -847,7 +855,7 @@ int launch_v6_one(const KParams &k, const FastHostTables &t, int *alias_in_kerne
     // in-place top rows inside the kernel: the band must start at row 0 with input row 0 present, and every
     // intermediate row the recurrence touches must still be in the ring after chunk 1 (rows -(a-1) .. 2*RB-a)
     *alias_in_kernel = 0;
-    if (k.alias_rows > 0 && k.out_row0 == 0 && k.in_row0 == 0 && k.alias_in_rows <= 2 * G::RB - A + 1 && k.alias_top_row <= 2 * G::RB - A - 1 &&
+    if (k.alias_rows > 0 && k.out_row0 == 0 && k.in_row0 == 0 && k.alias_in_rows <= std::min(2 * G::RB - A, 12) + 1 && k.alias_top_row <= std::min(2 * G::RB - A, 12) - 1 &&
         k.alias_rows <= k.out_rows) {
         p.alias_rows = k.alias_rows;
         p.alias_top_row = k.alias_top_row;
