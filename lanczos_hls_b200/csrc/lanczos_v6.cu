@@ -71,6 +71,10 @@ struct V6Params {
     int alias_rows, alias_top_row;   // in-place top rows done inside this kernel (0 = none / separate kernel)
     float align_k[8];         // phase-0 "cannot flip" constants
     int align_ki[8];          // the same, ceil(K * 2^16), for the integer re-check in the slow paths
+    // fp16x2 constants (both lanes equal, times 2^12) of the vectorised phase-0 re-check of the slow paths
+    // (phase0_doubt2): -K of the two negative residues, rounded away from zero; +K of the positive residues
+    // next to the centre, rounded toward zero (0 when the residue is not positive)
+    uint32_t p0_nk0, p0_nk4, p0_k1, p0_k3;
     float wtab[32 * 8];       // polyphase table [N][8] (padded to 8 taps), N <= 32, times 2^24
     double wdtab[8 * 8];      // double polyphase table [N][8] for N <= 8 (valid when uniform_*)
     unsigned long long *strict_counter;
@@ -209,6 +213,35 @@ __device__ __forceinline__ uint32_t hfma2_u(uint32_t a, uint32_t b, uint32_t c) 
     return d;
 }
 
+// Vectorised phase-0 re-check of the slow paths (a = 3: negative residues at taps 0 and 4, taps 1 and 3 positive).
+// Inputs: fp16x2 words with the bytes of taps 0, 1, 2 (centre v), 3, 4 as fp16 subnormals (byte * 2^-24).
+// Returns a word whose lane sign bits (0x8000 per lane) are set where the reference MAY return v - 1; a clear
+// bit proves that it returns v.  With H = 2^ceil(log2 v) (half the spacing of doubles below v is H * 2^-54,
+// fast_common.cuh phase0_safe) and K_k = |w_k| * 2^54, the running double sum of full_TB.h:58-63
+//   * is >= v after the centre tap if K_0 b_0 - K_1 b_1 <= H  (the two residues before the centre are added to
+//     each other first, the positive one offsets the negative one), and then
+//   * stays >= v if K_4 b_4 <= H, or if K_3 b_3 - K_4 b_4 >= 2H: tap 3 lifts the sum by at least
+//     K_3 b_3 - H' (H' = half the spacing ABOVE v <= 2H in these units) before tap 4 pulls it down.
+// Every test is one or two HFMA2: a single fp16 FMA rounds once and never changes the sign; where two are
+// chained, the constant of the second has 2^-10 of slack for the rounding of the first (host side).  The
+// constants carry the 0.99 margin of plan.cpp for the rounding of the reference's own products.
+__device__ __forceinline__ uint32_t phase0_doubt2(uint32_t b0, uint32_t b1, uint32_t v, uint32_t b3, uint32_t b4,
+                                                  uint32_t nk0, uint32_t k1, uint32_t k3, uint32_t nk4) {
+    const uint32_t v12 = hmul2_u(v, 0x6C006C00u);                      // v * 2^-12 (4096: exact)
+    const uint32_t t = hfma2_u(v12, 0x40004000u, 0x8C008C00u);         // (2v - 1) * 2^-12, exact
+    const uint32_t H = t & 0x7C007C00u;                                // 2^floor(log2(2v-1)) = H(v), times 2^-12 (v = 0: as v = 1)
+    const uint32_t nH2 = hmul2_u(H, 0xC000C000u);                      // -2H
+    const uint32_t zpre = hfma2_u(b1, k1, hfma2_u(b0, nk0, H));
+    const uint32_t z1 = hfma2_u(b4, nk4, H);
+    const uint32_t z2 = hfma2_u(b3, k3, hfma2_u(b4, nk4, nH2));
+    return (zpre | (z1 & z2)) & 0x80008000u;
+}
+
+// bit 7 of byte e (e = 0..3) -> bit e
+__device__ __forceinline__ uint32_t sign4_to_bits(uint32_t x) {
+    return ((((x >> 7) & 0x01010101u) * 0x01020408u) >> 24) & 0xfu;
+}
+
 // ---------------------------------------------------------------------------------------------
 // slow paths: executed by the thread that found a sample in doubt, kept out of line so that the hot loop
 // stays small.  Both restate full_TB.h:58-63 / :71-75 exactly (exact_taps).
@@ -226,6 +259,9 @@ template <int C, int A, int N, int D, int PH, int KM, int PAD_L>
 __device__ __noinline__ int h_fix(const V6Params &p, const HFixArgs a) {
     constexpr int TAPS = 2 * A;
     constexpr int NI = PH * (N - 1) * C;
+    // vectorised phase-0 re-check: written for a = 3 (residues of taps 0 and 4 negative) and layouts whose
+    // phase-0 centres are whole words
+    constexpr bool VEC0 = (A == 3) && (KM == 0x11) && (D == 1 || C == 4) && ((PH * C) % 4 == 0) && (PH * C <= 32) && (2 * C <= 8);
     int n_strict = 0;
     auto fix_byte = [&](int b, bool is_copy) {
         if (a.gbyte0 + b >= a.valid_bytes) return;
@@ -235,7 +271,7 @@ __device__ __noinline__ int h_fix(const V6Params &p, const HFixArgs a) {
         const int ph = (xx * D) % N;
         const uint8_t *tap0 = a.in_row + PAD_L + first * C + c - a.ibyte0;
         if (is_copy) {
-            if (phase0_safe<TAPS, KM>(tap0, C, p.align_ki)) return;
+            if (VEC0 ? tap0[(A - 1) * C] == 0 : phase0_safe<TAPS, KM>(tap0, C, p.align_ki)) return;
         } else {
             // the hot path's fp32 chain again (same order, same weights: same bits): only a sample whose
             // truncation really is in doubt needs the double evaluation
@@ -265,10 +301,46 @@ __device__ __noinline__ int h_fix(const V6Params &p, const HFixArgs a) {
         }
     }
     if (a.fix_z) {
+        if constexpr (VEC0) {
+            // all phase-0 samples of the item at once (phase0_doubt2, fp16x2): centre bytes are the item's own
+            // input bytes (D = 1) or the first pixel of every period (C = 4: whole words), tap k lies (k - 2) * C
+            // bytes away.  The item's input starts 8-byte aligned at in_row + PAD_L + g * IN_B.
+            constexpr int IN_B = PH * D * C, NCW = PH * C / 4, CSTEP = (C == 4) ? 4 * D : 4, NLW = (IN_B + 16) / 4;
+            const uint2 *src = reinterpret_cast<const uint2 *>(a.in_row + PAD_L + (a.gbyte0 / (N * C)) * (D * C) - 8);
+            uint32_t lw[NLW];
+#pragma unroll
+            for (int i = 0; i < NLW / 2; i++) {
+                const uint2 w = src[i];
+                lw[2 * i] = w.x;
+                lw[2 * i + 1] = w.y;
+            }
+            uint32_t doubt = 0;       // bit s: phase-0 sample s = per * C + c of the item
+#pragma unroll
+            for (int j = 0; j < NCW; j++) {
+                uint32_t lo[5], hi[5];
+#pragma unroll
+                for (int k = 0; k < 5; k++) {
+                    const int off = 8 + j * CSTEP + (k - 2) * C;        // byte offset of tap k of the word's first sample
+                    const uint32_t w = (off % 4 == 0) ? lw[off / 4] : __byte_perm(lw[off / 4], lw[off / 4 + 1], 0x3210u + 0x1111u * (off % 4));
+                    lo[k] = __byte_perm(w, 0u, 0x4140);
+                    hi[k] = __byte_perm(w, 0u, 0x4342);
+                }
+                const uint32_t dlo = phase0_doubt2(lo[0], lo[1], lo[2], lo[3], lo[4], p.p0_nk0, p.p0_k1, p.p0_k3, p.p0_nk4);
+                const uint32_t dhi = phase0_doubt2(hi[0], hi[1], hi[2], hi[3], hi[4], p.p0_nk0, p.p0_k1, p.p0_k3, p.p0_nk4);
+                doubt |= sign4_to_bits(__byte_perm(dlo, dhi, 0x7531)) << (4 * j);
+            }
 #pragma unroll 1
-        for (int per = 0; per < PH; per++)
+            for (; doubt; doubt &= doubt - 1) {
+                const int sidx = __ffs(doubt) - 1;
+                const int per = sidx / C, c = sidx - per * C;
+                fix_byte(per * N * C + c, true);
+            }
+        } else {
 #pragma unroll 1
-            for (int c = 0; c < C; c++) fix_byte(per * N * C + c, true);
+            for (int per = 0; per < PH; per++)
+#pragma unroll 1
+                for (int c = 0; c < C; c++) fix_byte(per * N * C + c, true);
+        }
     }
     return n_strict;
 }
@@ -317,6 +389,21 @@ __device__ __noinline__ int v_fix(const V6Params &p, const VFixArgs a) {
                 if ((dx >> (8 * e)) & 0xffu) need |= 1u << e;
                 if ((dy >> (8 * e)) & 0xffu) need |= 1u << (4 + e);
             }
+        } else if (A == 3 && KM == 0x11) {
+            // all 8 bytes of the row at once (fp16x2): which of them can the reference have turned into v - 1?
+            uint32_t hx[5][4];
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                const uint2 w = *reinterpret_cast<const uint2 *>(a.col + ((s0 + k) % RING) * SWM);
+                hx[k][0] = __byte_perm(w.x, 0u, 0x4140); hx[k][1] = __byte_perm(w.x, 0u, 0x4342);
+                hx[k][2] = __byte_perm(w.y, 0u, 0x4140); hx[k][3] = __byte_perm(w.y, 0u, 0x4342);
+            }
+            uint32_t dz[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) dz[i] = phase0_doubt2(hx[0][i], hx[1][i], hx[2][i], hx[3][i], hx[4][i], p.p0_nk0, p.p0_k1, p.p0_k3, p.p0_nk4);
+            // sign bits (bits 15 / 31 of dz[i] = bytes 2i / 2i+1) -> bit 7 of byte e, then one bit per byte
+            const uint32_t lo = __byte_perm(dz[0], dz[1], 0x7531), hi = __byte_perm(dz[2], dz[3], 0x7531);
+            need = sign4_to_bits(lo) | (sign4_to_bits(hi) << 4);
         } else {
             need = 0xffu;
         }
@@ -327,7 +414,7 @@ __device__ __noinline__ int v_fix(const V6Params &p, const VFixArgs a) {
             uint8_t taps_b[TAPS];
 #pragma unroll
             for (int k = 0; k < TAPS; k++) taps_b[k] = a.col[((s0 + k) % RING) * SWM + e];
-            if (ph == 0 && phase0_safe<TAPS, KM>(taps_b, 1, p.align_ki)) continue;
+            if (ph == 0 && (A == 3 && KM == 0x11 ? taps_b[A - 1] == 0 : phase0_safe<TAPS, KM>(taps_b, 1, p.align_ki))) continue;
             if (p.uniform_y && N <= 8) orow[e] = exact_taps<TAPS>(taps_b, 1, [&](int k) { return p.wdtab[ph * 8 + k]; });
             else orow[e] = exact_taps<TAPS>(taps_b, 1, [&](int k) { return p.wdy[(long long)y * TAPS + k]; });
             n_strict++;
@@ -784,6 +871,24 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+// fp16x2 word with both lanes = x rounded to fp16 away from zero (`away`) or toward zero
+uint32_t half2_bits(double x, bool away) {
+    const double ax = std::fabs(x);
+    uint32_t h = 0;
+    if (ax >= 65504.0) h = away ? 0x7C00u : 0x7BFFu;
+    else if (ax > 0) {
+        int e;
+        std::frexp(ax, &e);                    // ax = m * 2^e, m in [0.5, 1)
+        const int ex = std::max(e - 1, -14);   // fp16 exponent (subnormals share -14)
+        const double q = std::ldexp(ax, 10 - ex);              // in units of the fp16 spacing at this exponent
+        double m = away ? std::ceil(q) : std::floor(q);
+        // bits = (ex + 15) << 10 | (m - 1024) for normals; for subnormals (ex = -14, m < 1024) the exponent field is 0
+        h = (ax >= std::ldexp(1.0, -14)) ? (uint32_t)(((ex + 15) << 10) + ((int)m - 1024)) : (uint32_t)m;
+    }
+    if (x < 0) h |= 0x8000u;
+    return h | (h << 16);
+}
+
 template <int C, int A, int N, int D, int PH, int KM, int W, int MODE, bool ST64>
 int launch_v6_one(const KParams &k, const FastHostTables &t, int *alias_in_kernel, cudaStream_t s) {
     using G = Geo6<C, A, N, D, PH, W>;
@@ -863,6 +968,16 @@ int launch_v6_one(const KParams &k, const FastHostTables &t, int *alias_in_kerne
     }
     for (int i = 0; i < 8; i++) p.align_k[i] = i < 2 * A ? t.align_k[i] : 0.f;
     for (int i = 0; i < 8; i++) p.align_ki[i] = (int)std::ceil((double)p.align_k[i] * 65536.0 * 1.0001);
+    if (A == 3) {
+        // phase0_doubt2 constants: K = |w| * 2^54 (x 2^12 for the fp16 scale of the kernel); negative residues
+        // get the 1/0.99 margin and round away from zero, positive ones 0.99 * (1 - 2^-10) and round toward zero
+        const double *w0 = t.phase_wd;      // phase 0
+        const double S = std::ldexp(1.0, 54 + 12);
+        auto neg_k = [&](double w) { return w < 0 ? half2_bits(-(-w) * S / 0.99, true) : 0u; };
+        auto pos_k = [&](double w) { return w > 0 ? half2_bits(w * S * 0.99 * (1.0 - 1.0 / 1024.0), false) : 0u; };
+        p.p0_nk0 = neg_k(w0[0]); p.p0_nk4 = neg_k(w0[4]);
+        p.p0_k1 = pos_k(w0[1]); p.p0_k3 = pos_k(w0[3]);
+    }
     for (int ph = 0; ph < N; ph++)
         for (int q = 0; q < 8; q++) p.wtab[ph * 8 + q] = q < 2 * A ? t.phase_w[ph * 2 * A + q] * 16777216.f : 0.f;  // x 2^24, see kPixUnscale
     for (int ph = 0; ph < N && ph < 8; ph++)
