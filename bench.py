@@ -215,6 +215,7 @@ def run_bands(args, rank, local_rank, world):
     ms_per_step = t.item() / args.steps
 
     # end to end: the band's input rows from pinned host memory, the band's output rows back to it
+    lz.bind_host_to_device(local_rank)                   # pinned buffers land next to this rank's GPU
     hin = lz.PinnedBuffer(inn * iw * 3)
     hout = lz.PinnedBuffer((r1 - r0) * ow * 3)
     hin.array[:] = d_in.reshape(-1).cpu().numpy()
@@ -451,6 +452,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         Fe = min(args.e2e_frames, F)
+        numa_cpus = lz.bind_host_to_device(local_rank)      # pinned buffers below land next to this rank's GPU
         hin = lz.PinnedBuffer(Fe * IN_H * IN_W * CH)
         hout = lz.PinnedBuffer(Fe * OUT_H * OUT_W * CH)
         hin.array[:] = d_in[:Fe].reshape(-1).cpu().numpy() if Fe <= F else np.resize(d_in.reshape(-1).cpu().numpy(), hin.nbytes)
@@ -470,7 +472,8 @@ def main():
         e2e = {"value": n_gpus * Fe * e_steps * OUT_PX_PER_FRAME / te.item() / 1e6, "unit": "Mpix/s",
                "h2d_bytes_per_step": Fe * IN_H * IN_W * CH, "d2h_bytes_per_step": Fe * OUT_H * OUT_W * CH,
                "frames_per_step": Fe, "steps": e_steps, "ms_per_step": te.item() / e_steps * 1e3,
-               "api": "lanczos_b200_upscale_host (pinned host buffers, 3 streams)"}
+               "api": "lanczos_b200_upscale_host (pinned host buffers, 3 streams)",
+               "numa_bound_cpus": len(numa_cpus) if numa_cpus else 0}
         hin.free()
         hout.free()
 

@@ -17,6 +17,7 @@ from .api import (  # noqa: F401
     abi_version,
     alias_rows,
     band_input_rows,
+    bind_host_to_device,
     device_count,
     lanczos_expected,
     lanczos_stream,

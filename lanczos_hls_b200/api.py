@@ -213,6 +213,30 @@ def upscale(img, out_w, out_h, a=3, scale_n=0, scale_d=0, flags=0, device=0, n_s
     return out
 
 
+def bind_host_to_device(device=0):
+    """Pin the calling process to the CPUs next to GPU `device` (NVML CPU affinity), so that pinned host
+    buffers allocated afterwards are NUMA-local to the GPU's PCIe root.  With one process per GPU this keeps
+    the host-buffer path (lanczos_b200_upscale_host) from crossing the socket interconnect.  Returns the CPU
+    list, or None when NVML or the affinity call is unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(device)
+        bus = "%08x:%02x:%02x.0" % (getattr(props, "pci_domain_id", 0), props.pci_bus_id, props.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode() if hasattr(bus, "encode") else bus)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
+
+
 def upscale_bands_multi_gpu(img, out_w, out_h, devices, a=3, scale_n=0, scale_d=0, flags=0):
     """One large [H][W][C] host image split into row bands over `devices` (single process)."""
     img = np.ascontiguousarray(img, dtype=np.uint8)

@@ -663,7 +663,7 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
     for (int j = 0; j < NSLOT; j++)
 #pragma unroll
         for (int i = 0; i < VB; i++) acc[j][i] = 0.f;
-    // phase-0 filter delay line: fp16x2 words 8 * bytes * 2^-12 of the phase-0 rows 2 rows back
+    // phase-0 filter delay line: fp16x2 words (bytes * 2^-24) of the phase-0 rows 2 rows back
     constexpr int ZD = (D == 1) ? 2 : 1;                       // D = 1: rows r-1 and r-2 are both centres
     uint32_t zA[ZD][VB / 2];
 #pragma unroll
@@ -744,24 +744,22 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
                             }
                         }
                     }
-                    // ---- phase-0 "cannot flip" test, exact small-integer arithmetic on the fp16x2 pipe ----
+                    // ---- phase-0 "cannot flip" test on the fp16x2 pipe ----
                     // this row r is a phase-0 centre iff (s0 + A) % D == 0; with b = bytes * 2^-24 (fp16 subnormals):
-                    //   zpost(r-2) = 8*v[r-2] - 3*b[r]  and  zpre(r) = 8*v[r] - 3*b[r-2], both times 2^-12, both exact
-                    //   (|.| <= 2040 < 2^11).  K = 3/8 >= plan.cpp's K_k: negative means "may flip".
-                    //   Only 8*v*2^-12 is kept per row: -3*b[r-2] = -0.375 * (8*b[r-2]).
+                    //   zpost(r-2) = v[r-2] - 0.375*b[r]  and  zpre(r) = v[r] - 0.375*b[r-2]   (times 2^-24)
+                    //   One FMA each: the exact value (a multiple of 2^-27) is rounded once, to a multiple of 2^-24, and
+                    //   rounding never changes the sign (negative values round to a negative number or to -0).
+                    //   K = 3/8 >= plan.cpp's K_k: sign bit set means "may flip".  The delay line keeps the raw rows.
                     if (FILTER && (s0 + A) % D == 0) {
                         const int zs = (ZD == 2) ? (u & 1) : 0;       // D = 1: slot of row r-2 = slot this row overwrites
-                        const uint32_t kQ = 0x78007800u;              // 32768 = 8 * 2^12 (fp16x2)
-                        const uint32_t kP = 0xF200F200u;              // -12288 = -3 * 2^12
                         const uint32_t kR = 0xB600B600u;              // -0.375
                         const uint32_t hn[4] = {h0, h1, h2, h3};
                         uint32_t zpost = 0, zpre = 0;
 #pragma unroll
                         for (int i = 0; i < VB / 2; i++) {
-                            const uint32_t An = hmul2_u(hn[i], kQ);
-                            zpost |= hfma2_u(hn[i], kP, zA[zs][i]);
-                            zpre |= hfma2_u(zA[zs][i], kR, An);
-                            zA[zs][i] = An;
+                            zpost |= hfma2_u(hn[i], kR, zA[zs][i]);
+                            zpre |= hfma2_u(zA[zs][i], kR, hn[i]);
+                            zA[zs][i] = hn[i];
                         }
                         // output rows of centre r-2 = c+A-2 and of centre r = c+A, relative to yit (static)
                         if (zpost & 0x80008000u) fl |= 1u << (N * (G::S0 + u + A - 2) / D);
