@@ -182,6 +182,11 @@ double lanczos_b200_kernel(double x, int32_t a);
 /* Polyphase table of the plan: `phases` rows of 2a float weights (row p = phase p of the N-periodic
  * ratio, kernel.cpp:40-45's LUT restated per phase). Returns the number of phases or an error. */
 int lanczos_b200_phase_table(const lanczos_desc *desc, float *weights, int32_t capacity_floats);
+/* Introspection for tests: the four fp16x2 constants {-K0, +K1, +K3, -K4} (both lanes equal, times 2^12) of the
+ * phase-0 re-check that decides, for an output coordinate exactly on an input sample, whether the reference's
+ * double sum (full_TB.h:58-63, weights sin(k*pi)-residues ~1e-17) can fall below the centre value v and truncate
+ * to v-1 (a = 3 only; returns 4, or 0 and zeros for other a). tests/test_phase0_filter.py proves the test on CPU. */
+int lanczos_b200_phase0_constants(const lanczos_desc *desc, uint32_t *half2_consts);
 /* Number of top output rows that the reference's in-place pass aliases (0 with NO_ALIAS). */
 int lanczos_b200_alias_rows(const lanczos_desc *desc);
 

@@ -25,6 +25,7 @@ from .api import (  # noqa: F401
     lib_path,
     make_desc,
     phase_table,
+    phase0_constants,
     reduce_ratio,
     resolve,
     stats,

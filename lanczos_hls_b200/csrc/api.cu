@@ -202,7 +202,7 @@ int run_device(const DevicePlan &dp, unsigned flags, const uint8_t *d_in, uint8_
     int frc = -1;
     if (!(flags & LANCZOS_FLAG_GENERIC_KERNEL)) {
         FastHostTables t{h.phase_w.data(), h.phase_wd.data(), h.align_k.data(), h.x.aligned_exact ? 1 : 0,
-                         h.y.aligned_exact ? 1 : 0, h.x.uniform_phase ? 1 : 0, h.y.uniform_phase ? 1 : 0, h.x.i0.data()};
+                         h.y.aligned_exact ? 1 : 0, h.x.uniform_phase ? 1 : 0, h.y.uniform_phase ? 1 : 0, h.x.i0.data(), h.p0_half2};
         // development switch: LZB_IMPL=v5 selects the first-generation specialised kernels
         const char *impl = getenv("LZB_IMPL");
         if (!(impl && impl[0] == 'v' && impl[1] == '5')) frc = launch_v6(p, t, &kid, &alias_done, s);
@@ -327,6 +327,22 @@ int lanczos_b200_phase_table(const lanczos_desc *desc, float *weights, int32_t c
         memcpy(weights, p.phase_w.data(), sizeof(float) * need);
     }
     return d.scale_n;
+}
+
+int lanczos_b200_phase0_constants(const lanczos_desc *desc, uint32_t *half2_consts) {
+    if (!desc || !half2_consts) return LANCZOS_ERR_NULL;
+    lanczos_desc d = *desc;
+    int rc = resolve_desc(desc, &d);
+    if (rc != LANCZOS_OK) return rc;
+    lanczos_desc small = d;
+    small.in_w = small.in_h = d.scale_d;
+    small.out_w = small.out_h = d.scale_n;
+    small.in_pitch = small.out_pitch = 0;
+    Plan p;
+    rc = build_plan(&small, &p);
+    if (rc != LANCZOS_OK) return rc;
+    memcpy(half2_consts, p.p0_half2, sizeof(p.p0_half2));
+    return d.a == 3 ? 4 : 0;
 }
 
 int lanczos_b200_alias_rows(const lanczos_desc *desc) {

@@ -39,6 +39,7 @@ struct FastHostTables {            // host-side views of the plan the specialise
     int exact_x, exact_y;          // AxisTables.aligned_exact
     int uniform_x, uniform_y;      // AxisTables.uniform_phase
     const int32_t *i0x_host;       // [out_w] host copy of AxisTables.i0 (x axis)
+    const uint32_t *p0_half2;      // [4] Plan.p0_half2
 };
 int launch_fast(const KParams &p, const FastHostTables &t, int *kernel_id, cudaStream_t s);
 // Second generation of the same (lanczos_v6.cu): 8-byte V columns, PRMT-spliced copies, scalar constant-bank FFMA.

@@ -869,24 +869,6 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-// fp16x2 word with both lanes = x rounded to fp16 away from zero (`away`) or toward zero
-uint32_t half2_bits(double x, bool away) {
-    const double ax = std::fabs(x);
-    uint32_t h = 0;
-    if (ax >= 65504.0) h = away ? 0x7C00u : 0x7BFFu;
-    else if (ax > 0) {
-        int e;
-        std::frexp(ax, &e);                    // ax = m * 2^e, m in [0.5, 1)
-        const int ex = std::max(e - 1, -14);   // fp16 exponent (subnormals share -14)
-        const double q = std::ldexp(ax, 10 - ex);              // in units of the fp16 spacing at this exponent
-        double m = away ? std::ceil(q) : std::floor(q);
-        // bits = (ex + 15) << 10 | (m - 1024) for normals; for subnormals (ex = -14, m < 1024) the exponent field is 0
-        h = (ax >= std::ldexp(1.0, -14)) ? (uint32_t)(((ex + 15) << 10) + ((int)m - 1024)) : (uint32_t)m;
-    }
-    if (x < 0) h |= 0x8000u;
-    return h | (h << 16);
-}
-
 template <int C, int A, int N, int D, int PH, int KM, int W, int MODE, bool ST64>
 int launch_v6_one(const KParams &k, const FastHostTables &t, int *alias_in_kernel, cudaStream_t s) {
     using G = Geo6<C, A, N, D, PH, W>;
@@ -966,16 +948,7 @@ int launch_v6_one(const KParams &k, const FastHostTables &t, int *alias_in_kerne
     }
     for (int i = 0; i < 8; i++) p.align_k[i] = i < 2 * A ? t.align_k[i] : 0.f;
     for (int i = 0; i < 8; i++) p.align_ki[i] = (int)std::ceil((double)p.align_k[i] * 65536.0 * 1.0001);
-    if (A == 3) {
-        // phase0_doubt2 constants: K = |w| * 2^54 (x 2^12 for the fp16 scale of the kernel); negative residues
-        // get the 1/0.99 margin and round away from zero, positive ones 0.99 * (1 - 2^-10) and round toward zero
-        const double *w0 = t.phase_wd;      // phase 0
-        const double S = std::ldexp(1.0, 54 + 12);
-        auto neg_k = [&](double w) { return w < 0 ? half2_bits(-(-w) * S / 0.99, true) : 0u; };
-        auto pos_k = [&](double w) { return w > 0 ? half2_bits(w * S * 0.99 * (1.0 - 1.0 / 1024.0), false) : 0u; };
-        p.p0_nk0 = neg_k(w0[0]); p.p0_nk4 = neg_k(w0[4]);
-        p.p0_k1 = pos_k(w0[1]); p.p0_k3 = pos_k(w0[3]);
-    }
+    p.p0_nk0 = t.p0_half2[0]; p.p0_k1 = t.p0_half2[1]; p.p0_k3 = t.p0_half2[2]; p.p0_nk4 = t.p0_half2[3];
     for (int ph = 0; ph < N; ph++)
         for (int q = 0; q < 8; q++) p.wtab[ph * 8 + q] = q < 2 * A ? t.phase_w[ph * 2 * A + q] * 16777216.f : 0.f;  // x 2^24, see kPixUnscale
     for (int ph = 0; ph < N && ph < 8; ph++)

@@ -24,6 +24,23 @@ static double sinc_ref(double x) {
 // full_TB.h:51-53 (LANCZOS_A is an int macro: M_PI*x/a divides by (double)a)
 double ref_kernel(double x, int a) { return sinc_ref(M_PI * x) * sinc_ref(M_PI * x / a); }
 
+uint32_t half2_bits(double x, bool away) {
+    const double ax = std::fabs(x);
+    uint32_t h = 0;
+    if (ax >= 65504.0) h = away ? 0x7C00u : 0x7BFFu;
+    else if (ax > 0) {
+        int e;
+        std::frexp(ax, &e);                    // ax = m * 2^e, m in [0.5, 1)
+        const int ex = std::max(e - 1, -14);   // fp16 exponent (subnormals share -14)
+        const double q = std::ldexp(ax, 10 - ex);              // in units of the fp16 spacing at this exponent
+        const double m = away ? std::ceil(q) : std::floor(q);
+        // normals: (ex + 15) << 10 | (m - 1024), a carry into the exponent included; subnormals: m itself
+        h = (ax >= std::ldexp(1.0, -14)) ? (uint32_t)(((ex + 15) << 10) + ((int)m - 1024)) : (uint32_t)m;
+    }
+    if (x < 0) h |= 0x8000u;
+    return h | (h << 16);
+}
+
 int resolve_desc(const lanczos_desc *in, lanczos_desc *out) {
     if (!in || !out) return LANCZOS_ERR_NULL;
     lanczos_desc d = *in;
@@ -157,6 +174,24 @@ int build_plan(const lanczos_desc *desc, Plan *out) {
             const double K = -w * std::ldexp(1.0, 54) / 0.99;
             if (K > 1e-7) p.align_k[k] = (float)(K * (1.0 + 1e-6));
         }
+    }
+    // Sharper phase-0 test of the slow paths (lanczos_v6.cu phase0_doubt2), a = 3: with H = 2^ceil(log2 v) and
+    // K_k = |w_k| * 2^54 the reference returns v if  K0 b0 - K1 b1 <= H  and  (K4 b4 <= H  or  K3 b3 - K4 b4 >= 2H).
+    // Negative residues get the 1/0.99 margin (rounding of the reference's own products) and are rounded away
+    // from zero; positive ones get 0.99 * (1 - 2^-10) (the second factor covers the rounding of the first of
+    // two chained fp16 FMAs) and are rounded toward zero.  A residue with the wrong sign disables its term.
+    if (a == 3) {
+        const double *w0 = p.phase_wd.data();       // phase 0
+        const double S = std::ldexp(1.0, 54 + 12);  // the kernel's fp16 values carry 2^-12
+        auto neg_k = [&](double w) { return half2_bits(w * S / 0.99, true); };
+        auto pos_k = [&](double w) { return half2_bits(w * S * 0.99 * (1.0 - 1.0 / 1024.0), false); };
+        // the argument holds for this sign pattern only (taps 0 and 4 pull down, 1 and 3 lift, tap 5 is far
+        // below half an ulp of 1); anything else: every sample stays in doubt (-inf constants)
+        const bool pattern = w0[0] < 0 && w0[4] < 0 && w0[1] > 0 && w0[3] > 0 && w0[2] == 1.0 && std::fabs(w0[5]) < 1e-25;
+        p.p0_half2[0] = pattern ? neg_k(w0[0]) : 0xFC00FC00u;
+        p.p0_half2[1] = pattern ? pos_k(w0[1]) : 0u;
+        p.p0_half2[2] = pattern ? pos_k(w0[3]) : 0u;
+        p.p0_half2[3] = pattern ? neg_k(w0[4]) : 0xFC00FC00u;
     }
     rc = build_axis(p.x, p.d.out_w, p.d.in_w, a, n, dd, p.phase_w, p.phase_wd);
     if (rc != LANCZOS_OK) return rc;
