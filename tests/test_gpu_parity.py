@@ -311,3 +311,19 @@ def test_config4_shape_4k_to_8k_one_frame(torch_cuda, lz, oracle):
     want = oracle.upscale(img, 7680, 4320, 3, 2, 1)
     got = gpu_upscale(torch_cuda, lz, img, 7680, 4320, 3, 2, 1)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("cfg", [  # in_w, in_h, out_w, out_h, n, d, a, c: output sizes that are NOT in * N / D
+    (64, 48, 120, 100, 2, 1, 3, 3), (64, 48, 140, 90, 2, 1, 3, 3), (240, 60, 484, 118, 2, 1, 3, 3),
+    (90, 64, 132, 100, 3, 2, 3, 4), (50, 40, 80, 70, 17, 10, 3, 3), (33, 29, 70, 40, 2, 1, 2, 1),
+])
+@pytest.mark.parametrize("kind", ["noise", "smooth"])
+def test_output_size_independent_of_ratio(torch_cuda, lz, oracle, cfg, kind):
+    """OUT_WIDTH / OUT_HEIGHT are loop bounds only in the reference (full_TB.h:56,69): the ratio comes from
+    SCALE_N / SCALE_D, and coordinates past the last input sample just lose taps (full_TB.h:59,72)."""
+    iw, ih, ow, oh, n, d, a, c = cfg
+    img = {"noise": noise_hwc, "smooth": smooth_hwc}[kind](oracle, ih, iw, c, seed=iw + oh)
+    want = oracle.upscale(img, ow, oh, a, n, d)
+    got = gpu_upscale(torch_cuda, lz, img, ow, oh, a, n, d)
+    st = diff_stats(got, want)
+    assert st["max"] == 0, st
