@@ -115,6 +115,16 @@ int lanczos_b200_upscale_batch(const lanczos_desc *desc, const uint8_t *d_in, ui
                                int32_t n_frames, int64_t in_frame_stride,
                                int64_t out_frame_stride, int device, void *cuda_stream);
 
+/* ---- planar device buffers: the layout of the reference's software twin itself,
+ * `lanczos_expected(byte img_in[C][IN_H][IN_W], byte img_out[C][OUT_H][OUT_W])` (full_TB.h:20-21, 79-96).
+ * `desc->channels` = planes per frame; `in_pitch`/`out_pitch` = row pitch of a plane in bytes (0 = width).
+ * Plane q (q = frame*channels + c) lives at d_in + q*in_plane_stride / d_out + q*out_plane_stride
+ * (0 = pitch*height). Every plane is resampled as a one-channel image, like the reference's per-channel loops
+ * (full_TB.h:83-95); one launch covers all planes of all frames. */
+int lanczos_b200_upscale_planar(const lanczos_desc *desc, const uint8_t *d_in, uint8_t *d_out,
+                                int32_t n_frames, int64_t in_plane_stride, int64_t out_plane_stride,
+                                int device, void *cuda_stream);
+
 /* ---- one row band of a large image (BASELINE config 5).
  * Computes output rows [out_row0, out_row0+out_rows) of the image described by `desc`.
  * `d_in_band` points at input row `in_row0` of the image and holds `in_rows` rows; they must

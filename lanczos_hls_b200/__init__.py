@@ -35,6 +35,7 @@ from .api import (  # noqa: F401
     upscale_device,
     upscale_batch_device,
     upscale_band_device,
+    upscale_planar_device,
     PinnedBuffer,
     hls_lut,
     upscale_hls_device,

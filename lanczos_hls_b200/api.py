@@ -62,6 +62,7 @@ def lib():
     i32, i64 = C.c_int32, C.c_int64
     L.lanczos_b200_upscale.argtypes = [dp, u8p, u8p, C.c_int, vp]
     L.lanczos_b200_upscale_batch.argtypes = [dp, u8p, u8p, i32, i64, i64, C.c_int, vp]
+    L.lanczos_b200_upscale_planar.argtypes = [dp, u8p, u8p, i32, i64, i64, C.c_int, vp]
     L.lanczos_b200_upscale_band.argtypes = [dp, u8p, u8p, i32, i32, i32, i32, C.c_int, vp]
     L.lanczos_b200_band_input_rows.argtypes = [dp, i32, i32, C.POINTER(i32), C.POINTER(i32)]
     L.lanczos_b200_upscale_host.argtypes = [dp, u8p, u8p, i32, i64, i64, C.c_int, i32]
@@ -291,6 +292,21 @@ def upscale_batch_device(d_in, d_out, a=3, scale_n=0, scale_d=0, flags=0):
     _check(lib().lanczos_b200_upscale_batch(C.byref(desc), C.c_void_p(d_in.data_ptr()), C.c_void_p(d_out.data_ptr()),
                                             f, d_in.stride(0), d_out.stride(0), d_in.device.index or 0,
                                             _stream_ptr(d_in)))
+    return d_out
+
+
+def upscale_planar_device(d_in, d_out, a=3, scale_n=0, scale_d=0, flags=0):
+    """torch uint8 CUDA tensors [C][H][W] -> [C][OH][OW] or [F][C][H][W] -> [F][C][OH][OW]: the layout of the
+    reference's lanczos_expected arguments (full_TB.h:20-21), every plane resampled on its own."""
+    if d_in.dim() == 3:
+        d_in, d_out = d_in.unsqueeze(0), d_out.unsqueeze(0)
+    f, c, h, w = d_in.shape
+    _, _, oh, ow = d_out.shape
+    assert d_in.stride(0) == c * d_in.stride(1) and d_out.stride(0) == c * d_out.stride(1), "planes must be equally spaced"
+    desc = make_desc(w, h, ow, oh, c, a, scale_n, scale_d, d_in.stride(2), d_out.stride(2), flags)
+    _check(lib().lanczos_b200_upscale_planar(C.byref(desc), C.c_void_p(d_in.data_ptr()), C.c_void_p(d_out.data_ptr()),
+                                             f, d_in.stride(1), d_out.stride(1), d_in.device.index or 0,
+                                             _stream_ptr(d_in)))
     return d_out
 
 

@@ -438,6 +438,18 @@ int lanczos_b200_upscale(const lanczos_desc *desc, const uint8_t *d_in, uint8_t 
     return lanczos_b200_upscale_batch(desc, d_in, d_out, 1, 0, 0, device, cuda_stream);
 }
 
+int lanczos_b200_upscale_planar(const lanczos_desc *desc, const uint8_t *d_in, uint8_t *d_out, int32_t n_frames,
+                                int64_t in_plane_stride, int64_t out_plane_stride, int device, void *cuda_stream) {
+    if (!desc || !d_in || !d_out) return LANCZOS_ERR_NULL;
+    if (n_frames < 0) return LANCZOS_ERR_DIMS;
+    if (desc->channels < 1 || desc->channels > 4) return LANCZOS_ERR_CHANNELS;
+    // a plane is a one-channel frame: the reference's own loop is per channel, rows then columns (full_TB.h:83-95)
+    lanczos_desc plane = *desc;
+    plane.channels = 1;
+    return lanczos_b200_upscale_batch(&plane, d_in, d_out, n_frames * desc->channels, in_plane_stride, out_plane_stride,
+                                      device, cuda_stream);
+}
+
 int lanczos_b200_upscale_band(const lanczos_desc *desc, const uint8_t *d_in_band, uint8_t *d_out_band,
                               int32_t out_row0, int32_t out_rows, int32_t in_row0, int32_t in_rows,
                               int device, void *cuda_stream) {
@@ -636,26 +648,22 @@ int lanczos_b200_expected(const lanczos_desc *desc, const uint8_t *h_in_planar, 
     if (!desc || !h_in_planar || !h_out_planar) return LANCZOS_ERR_NULL;
     lanczos_desc d = *desc;
     d.in_pitch = d.out_pitch = 0;  // planar arrays are dense (full_TB.h:20-21)
+    lanczos_desc r;
+    int rc = resolve_desc(&d, &r);
+    if (rc != LANCZOS_OK) return rc;
     DeviceGuard g(device);
     if (!g.ok) return cuda_fail(cudaErrorInvalidDevice, "cudaSetDevice");
-    std::shared_ptr<DevicePlan> dp;
-    int rc = get_plan(&d, device, &dp);
-    if (rc != LANCZOS_OK) return rc;
-    const lanczos_desc &r = dp->host.d;
+    // planes stay planes: each one is upscaled as a one-channel frame (no interleaving round trip)
+    d.in_pitch = d.out_pitch = 0;
     const size_t in_bytes = (size_t)r.in_w * r.in_h * r.channels, out_bytes = (size_t)r.out_w * r.out_h * r.channels;
-    Scratch pin(device, in_bytes), iin(device, in_bytes), iout(device, out_bytes), pout(device, out_bytes);
-    if (!pin.p || !iin.p || !iout.p || !pout.p) return LANCZOS_ERR_NOMEM;
+    Scratch pin(device, in_bytes), pout(device, out_bytes);
+    if (!pin.p || !pout.p) return LANCZOS_ERR_NOMEM;
     cudaStream_t s = nullptr;
     CU(cudaMemcpyAsync(pin.p, h_in_planar, in_bytes, cudaMemcpyHostToDevice, s));
-    CU((cudaError_t)launch_planar_to_interleaved((const uint8_t *)pin.p, (uint8_t *)iin.p, r.in_w, r.in_h, r.channels, s));
-    rc = run_device(*dp, d.flags, (const uint8_t *)iin.p, (uint8_t *)iout.p, 1, 0, 0, 0, r.out_h, 0, r.in_h,
-                    r.in_pitch, r.out_pitch, s);
+    rc = lanczos_b200_upscale_planar(&d, (const uint8_t *)pin.p, (uint8_t *)pout.p, 1, 0, 0, device, s);
     if (rc != LANCZOS_OK) return rc;
-    const int64_t launches = g_stats.kernel_launches + 2;
-    CU((cudaError_t)launch_interleaved_to_planar((const uint8_t *)iout.p, (uint8_t *)pout.p, r.out_w, r.out_h, r.channels, s));
     CU(cudaMemcpyAsync(h_out_planar, pout.p, out_bytes, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
-    g_stats.kernel_launches = launches;
     return LANCZOS_OK;
 }
 

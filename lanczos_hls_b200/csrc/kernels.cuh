@@ -53,9 +53,7 @@ int launch_alias_rows(const KParams &p, cudaStream_t s);
 int launch_hls(const uint8_t *in, uint8_t *out, long long in_pitch, long long out_pitch, long long in_fs,
                long long out_fs, int n_frames, int in_w, int in_h, int out_w, int out_h, int channels, int a, int n,
                int bp, const int *lut, cudaStream_t s);
-// Planar <-> interleaved helpers for lanczos_b200_expected / lanczos_b200_stream.
-int launch_planar_to_interleaved(const uint8_t *planar, uint8_t *inter, int w, int h, int c, cudaStream_t s);
-int launch_interleaved_to_planar(const uint8_t *inter, uint8_t *planar, int w, int h, int c, cudaStream_t s);
+// Packed 24-bit words <-> interleaved RGB for lanczos_b200_stream.
 int launch_words_to_rgb(const uint32_t *words, uint8_t *rgb, long long n_px, cudaStream_t s);
 int launch_rgb_to_words(const uint8_t *rgb, uint32_t *words, long long n_px, cudaStream_t s);
 

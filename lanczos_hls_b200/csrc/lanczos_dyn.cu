@@ -502,6 +502,7 @@ int launch_dyn(const KParams &k, const FastHostTables &t, int *kernel_id, cudaSt
     LZD_CASE(3, 3, 17, 10, 5)
     LZD_CASE(3, 3, 3, 2, 6)
     LZD_CASE(3, 3, 3, 1, 7)
+    LZD_CASE(1, 3, 17, 10, 11)
 #undef LZD_CASE
     return -1;
 }

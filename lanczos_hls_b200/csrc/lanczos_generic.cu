@@ -169,20 +169,6 @@ __global__ void __launch_bounds__(128) lanczos_alias_rows_kernel(const KParams p
 }
 
 // ---- layout helpers --------------------------------------------------------------------------
-__global__ void planar_to_interleaved_kernel(const uint8_t *planar, uint8_t *inter, long long n_px, int c) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_px * c) return;
-    const long long px = i / c;
-    const int ch = (int)(i - px * c);
-    inter[i] = planar[(long long)ch * n_px + px];
-}
-__global__ void interleaved_to_planar_kernel(const uint8_t *inter, uint8_t *planar, long long n_px, int c) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_px * c) return;
-    const long long ch = i / n_px;
-    const long long px = i - ch * n_px;
-    planar[i] = inter[px * c + ch];
-}
 // worker.cpp:35-43 packing: channel i in bits [8i+7:8i] of the stream word
 __global__ void words_to_rgb_kernel(const uint32_t *words, uint8_t *rgb, long long n_px) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -219,16 +205,6 @@ int launch_alias_rows(const KParams &p, cudaStream_t s) {
     return (int)cudaGetLastError();
 }
 
-int launch_planar_to_interleaved(const uint8_t *planar, uint8_t *inter, int w, int h, int c, cudaStream_t s) {
-    const long long n = (long long)w * h;
-    planar_to_interleaved_kernel<<<(unsigned)((n * c + 255) / 256), 256, 0, s>>>(planar, inter, n, c);
-    return (int)cudaGetLastError();
-}
-int launch_interleaved_to_planar(const uint8_t *inter, uint8_t *planar, int w, int h, int c, cudaStream_t s) {
-    const long long n = (long long)w * h;
-    interleaved_to_planar_kernel<<<(unsigned)((n * c + 255) / 256), 256, 0, s>>>(inter, planar, n, c);
-    return (int)cudaGetLastError();
-}
 int launch_words_to_rgb(const uint32_t *words, uint8_t *rgb, long long n_px, cudaStream_t s) {
     words_to_rgb_kernel<<<(unsigned)((n_px + 255) / 256), 256, 0, s>>>(words, rgb, n_px);
     return (int)cudaGetLastError();

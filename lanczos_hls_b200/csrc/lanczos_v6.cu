@@ -994,6 +994,10 @@ int launch_v6(const KParams &k, const FastHostTables &t, int *kernel_id, int *al
     LZ6_CASE(4, 3, 2, 1, 6, 0x11, 2)
     LZ6_CASE(4, 3, 3, 2, 4, 0x11, 3)
     LZ6_CASE(3, 2, 2, 1, 8, 0x0, 4)
+    // planar images (lanczos_b200_upscale_planar): every plane is a one-channel frame
+    LZ6_CASE(1, 3, 2, 1, 24, 0x11, 8)
+    LZ6_CASE(1, 3, 3, 2, 16, 0x11, 9)
+    LZ6_CASE(1, 2, 2, 1, 24, 0x0, 10)
 #undef LZ6_CASE
     return -1;
 }

@@ -327,3 +327,38 @@ def test_output_size_independent_of_ratio(torch_cuda, lz, oracle, cfg, kind):
     got = gpu_upscale(torch_cuda, lz, img, ow, oh, a, n, d)
     st = diff_stats(got, want)
     assert st["max"] == 0, st
+
+
+PLANAR = [  # in_w, in_h, n, d, a, planes, expected kernel_id (0 = generic)
+    (960, 540, 2, 1, 3, 3, 8), (240, 97, 2, 1, 3, 3, 8), (96, 54, 2, 1, 3, 1, 8), (640, 360, 3, 2, 3, 4, 9),
+    (496, 301, 2, 1, 2, 3, 10), (240, 120, 17, 10, 3, 3, 11), (131, 77, 2, 1, 3, 3, 0), (90, 50, 5, 3, 3, 2, 0),
+]
+
+
+@pytest.mark.parametrize("cfg", PLANAR, ids=lambda c: "x".join(map(str, c)))
+@pytest.mark.parametrize("kind", ["noise", "smooth", "dark"])
+def test_planar_device_api_bit_exact(torch_cuda, lz, oracle, cfg, kind):
+    """lanczos_b200_upscale_planar takes the arrays of lanczos_expected (full_TB.h:20-21, 79-96) as they are."""
+    iw, ih, n, d, a, c, kid = cfg
+    ow, oh = oracle.out_dims(iw, ih, n, d)
+    img = planar({"noise": noise_hwc, "smooth": smooth_hwc, "dark": dark_hwc}[kind](oracle, ih, iw, c, seed=iw))
+    want = oracle.expected_planar(img, ow, oh, a, n, d, fast=True)
+    d_in = torch_cuda.from_numpy(img).cuda()
+    d_out = torch_cuda.empty((c, oh, ow), dtype=torch_cuda.uint8, device="cuda")
+    lz.upscale_planar_device(d_in, d_out, a=a, scale_n=n, scale_d=d)
+    torch_cuda.cuda.synchronize()
+    assert lz.stats()["kernel_id"] == kid
+    st = diff_stats(d_out.cpu().numpy(), want)
+    assert st["max"] == 0, st
+
+
+def test_planar_batch_of_frames(torch_cuda, lz, oracle):
+    f, c, ih, iw = 3, 3, 54, 96
+    imgs = np.stack([planar(noise_hwc(oracle, ih, iw, c, seed=40 + i)) for i in range(f)])
+    d_in = torch_cuda.from_numpy(imgs).cuda()
+    d_out = torch_cuda.empty((f, c, 108, 192), dtype=torch_cuda.uint8, device="cuda")
+    lz.upscale_planar_device(d_in, d_out, a=3)
+    torch_cuda.cuda.synchronize()
+    got = d_out.cpu().numpy()
+    for i in range(f):
+        assert np.array_equal(got[i], oracle.expected_planar(imgs[i], 192, 108, 3, 2, 1, fast=True))
