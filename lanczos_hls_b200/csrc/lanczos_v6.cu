@@ -490,6 +490,9 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
     constexpr int NSLOT = nslot6<N, D, TAPS>();
     constexpr int CNTMAX = cmax6(1, cmax6(cnt6<N, D>(0), cnt6<N, D>(D - 1)));   // D <= 2
     constexpr bool FILTER = (MODE == 0) && (KM != 0);
+    // input rows per V loop iteration: one (even) ratio period; the plain fp32 V pass of MODE 1 is small enough to
+    // take two of them per iteration at D = 1 (no loop-carried register moves left: +2 % measured)
+    constexpr int VU = (MODE == 1 && D == 1 && G::RB % (2 * G::U) == 0) ? 2 * G::U : G::U;
     static_assert(KM == 0 || (A == 3 && KM == 0x11), "phase-0 row filter is written for the +-2 residues of a = 3");
     extern __shared__ __align__(128) uint8_t smem_raw[];
     // every warp works on its own strip with its own TMA stages, ring and barriers: nothing is shared between
@@ -692,14 +695,14 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
             uint8_t *op = ocol + (long long)ylo6<N, D>(G::S0) * opitch;   // next output row (rows come out in order)
             int yit = ybase;
             // centre rows of phase-0 outputs lie A rows back; for the first A rows of a chunk that is the previous region
-            int wrapseq[G::U];
+            int wrapseq[VU];
 #pragma unroll
-            for (int u = 0; u < G::U; u++) wrapseq[u] = wrapoff;
+            for (int u = 0; u < VU; u++) wrapseq[u] = wrapoff;
 #pragma unroll 1
-            for (int it = 0; it < G::RB / G::U; it++) {
+            for (int it = 0; it < G::RB / VU; it++) {
                 uint32_t fl = 0;                               // flags of this iteration, bit = row - yit
 #pragma unroll
-                for (int u = 0; u < G::U; u++) {
+                for (int u = 0; u < VU; u++) {
                     const int s0 = (G::S0 + u) % D, tq = (G::S0 + u) / D;   // completing centre = D*(t + tq) + s0
                     const int cnt0 = cnt6<N, D>(s0);
                     const uint2 w = *reinterpret_cast<const uint2 *>(vit + u * SWM);
@@ -804,12 +807,12 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
                         }
                     }
                 }
-                if (MODE == 0) fixrows |= (unsigned long long)fl << (it * (N * G::U / D));
-                vit += G::U * SWM;
-                yit += N * G::U / D;
+                if (MODE == 0) fixrows |= (unsigned long long)fl << (it * (N * VU / D));
+                vit += VU * SWM;
+                yit += N * VU / D;
                 // rows lr-A of the next iteration: one more iteration's worth of them lies inside this chunk
 #pragma unroll
-                for (int u = 0; u < G::U; u++) wrapseq[u] = (u + G::U * (it + 1) - A >= 0) ? 0 : wrapseq[u];
+                for (int u = 0; u < VU; u++) wrapseq[u] = (u + VU * (it + 1) - A >= 0) ? 0 : wrapseq[u];
             }
         };
         if (interior) body(std::false_type{}); else body(std::true_type{});
