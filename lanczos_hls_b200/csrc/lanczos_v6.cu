@@ -884,8 +884,11 @@ int launch_v6_one(const KParams &k, const FastHostTables &t, int *alias_in_kerne
     const int strips = (row_bytes + sw - 1) / sw;
     const int vperiod0 = k.out_row0 / N;
     const int vperiods = (k.out_row0 + k.out_rows + N - 1) / N - vperiod0;
-    // vertical segments: every segment re-runs 2a-1 warm-up rows, every partial last wave idles SMs.
-    // Pick the count that minimises (waves) x (rows per segment + warm-up).
+    // Vertical segments: every segment re-runs 2a-1 warm-up rows and works in whole chunks of RB rows, and the
+    // time of a chunk depends on how many warps share an SM sub-partition: measured on 1080p->2160p single
+    // frames (LZB_SEGS sweep, B200) it is ~(1.6 + 1.7 w) us for w = 1..4 resident warps -- two warps already
+    // reach 92 % of the issue rate of four.  Small jobs minimise chunks x sum over waves of that time; batches,
+    // which run many waves, minimise waves x rows per segment.
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -909,10 +912,21 @@ int launch_v6_one(const KParams &k, const FastHostTables &t, int *alias_in_kerne
     for (int sg = 1; sg <= std::min(max_segs, 256); sg++) {
         const int per = (vperiods + sg - 1) / sg;
         const int sg_eff = (vperiods + per - 1) / per;
-        const double rows = (double)per * D + 2 * A - 1 + 0.5 * G::RB;      // + pipeline fill
-        const double waves = std::ceil((double)(cols * sg_eff) / (double)slots);
-        // a wave that is not full still costs a full wave unless it is the only one
-        const double cost = (cols * sg_eff <= slots) ? rows * 1.0 : rows * waves;
+        double cost;
+        if (cols * 4 <= slots) {
+            // small job (a frame or a few): everything is resident at once, latency counts
+            const double chunks = std::ceil((double)(per * D + 2 * A - 1) / G::RB);
+            const long long ctas = cols * sg_eff;
+            const long long full_waves = ctas / slots, rem = ctas - full_waves * slots;
+            auto chunk_time = [&](double warps) { return 1.6 + 1.7 * std::max(1.0, warps / (4.0 * sms)); };
+            cost = chunks * ((double)full_waves * chunk_time((double)slots) + (rem > 0 ? chunk_time((double)rem) : 0.0));
+        } else {
+            // batch: (waves) x (rows per segment + warm-up + pipeline fill); a wave that is not full still costs a
+            // full wave unless it is the only one
+            const double rows = (double)per * D + 2 * A - 1 + 0.5 * G::RB;
+            const double waves = std::ceil((double)(cols * sg_eff) / (double)slots);
+            cost = (cols * sg_eff <= slots) ? rows * 1.0 : rows * waves;
+        }
         if (cost < best_cost - 1e-9) { best_cost = cost; segs = sg_eff; }
     }
     if (force_segs > 0) segs = std::min(force_segs, max_segs);

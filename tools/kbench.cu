@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 #include <cuda_runtime.h>
@@ -100,6 +101,43 @@ int main(int argc, char **argv) {
         CK(cudaEventSynchronize(e1));
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
         best = ms < best ? ms : best; total += ms;
+    }
+    // back-to-back launches (no host synchronisation in between): per-call time = max(host issue time, GPU time)
+    {
+        CK(cudaDeviceSynchronize());
+        timespec t0, t1;
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        CK(cudaEventRecord(e0));
+        for (int i = 0; i < iters; i++) lanczos_b200_upscale_batch(&desc, d_in, d_out, frames, 0, 0, 0, nullptr);
+        CK(cudaEventRecord(e1));
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double host_us = ((t1.tv_sec - t0.tv_sec) * 1e9 + (t1.tv_nsec - t0.tv_nsec)) / 1e3 / iters;
+        printf("   back to back: %.2f us per call on the GPU timeline, %.2f us of host time per call\n", ms * 1e3 / iters, host_us);
+    }
+    // the same frames as single-frame launches (one call per frame, buffers rotate through the whole batch so the
+    // working set stays larger than L2), on 1 stream and round-robin over 4 streams
+    if (frames >= 8) {
+        cudaStream_t st[4];
+        for (int i = 0; i < 4; i++) CK(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+        for (int ns = 1; ns <= 4; ns *= 2) {
+            CK(cudaDeviceSynchronize());
+            const int calls = iters * frames;
+            CK(cudaEventRecord(e0, st[0]));
+            for (int i = 1; i < ns; i++) CK(cudaStreamWaitEvent(st[i], e0, 0));
+            for (int i = 0; i < calls; i++) {
+                const int f = i % frames;
+                lanczos_b200_upscale(&desc, d_in + in_frame * f, d_out + out_frame * f, 0, st[i % ns]);
+            }
+            cudaEvent_t ej[4];
+            for (int i = 1; i < ns; i++) { CK(cudaEventCreate(&ej[i])); CK(cudaEventRecord(ej[i], st[i])); CK(cudaStreamWaitEvent(st[0], ej[i], 0)); }
+            CK(cudaEventRecord(e1, st[0]));
+            CK(cudaEventSynchronize(e1));
+            float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+            printf("   single-frame launches over %d frames, %d stream(s): %.2f us per frame = %.1f Gpix/s\n", frames, ns, ms * 1e3 / calls,
+                   (double)ow * oh / (ms * 1e-3 / calls) / 1e9);
+        }
     }
     const double opx = (double)ow * oh * frames;
     const double bytes = (double)(in_frame + out_frame) * frames;
