@@ -446,6 +446,45 @@ def main():
             tol["max_abs_diff"] = int((d_out.to(torch.int16) - ref_out.to(torch.int16)).abs().max().item())
             del neq, ref_out
 
+    # ---- BASELINE configs[1] read literally: ONE frame per call (lanczos_b200_upscale), the frames of the batch in
+    # turn so the working set stays larger than L2; on one stream and round-robin over four ----
+    single = None
+    if args.workload in WORKLOADS:
+        import ctypes as C
+        L = lz.lib()
+        desc = lz.make_desc(IN_W, IN_H, OUT_W, OUT_H, CH, A, SN, SD, flags=args.flags)
+        in_fs, out_fs = d_in.stride(0), d_out.stride(0)
+        in0, out0 = d_in.data_ptr(), d_out.data_ptr()
+        ptrs = [(C.c_void_p(in0 + f * in_fs), C.c_void_p(out0 + f * out_fs)) for f in range(F)]
+        streams = [torch.cuda.Stream(device=dev) for _ in range(4)]
+        sp = [C.c_void_p(st.cuda_stream) for st in streams]
+        dref = C.byref(desc)
+        single = {"call": "lanczos_b200_upscale, one frame per launch, frames of the batch in turn"}
+        rounds = max(2, min(args.steps, 10))
+        for ns in (1, 4):
+            def run():
+                i = 0
+                for _ in range(rounds):
+                    for pi, po in ptrs:
+                        L.lanczos_b200_upscale(dref, pi, po, local_rank, sp[i % ns])
+                        i += 1
+            run()
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record(streams[0])
+            for st in streams[1:ns]:
+                st.wait_event(s0)
+            run()
+            for st in streams[1:ns]:
+                streams[0].wait_stream(st)
+            s1.record(streams[0])
+            barrier()
+            tsf = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+            if dist is not None:
+                dist.all_reduce(tsf, op=dist.ReduceOp.MAX)
+            us = tsf.item() * 1e3 / (rounds * F)
+            single["streams_%d" % ns] = {"value": n_gpus * OUT_PX_PER_FRAME / (us * 1e-6) / 1e6, "unit": "Mpix/s", "us_per_frame": us}
+
     clocks = sampler.stop() if rank == 0 else None      # sampled over the timed device loops above
 
     # ---- end to end through the host-buffer C-ABI call (pinned host memory) ----
@@ -502,6 +541,7 @@ def main():
                    "l2": f"inputs larger than L2: {F * ALGO_BYTES_PER_FRAME / 1e6:.0f} MB streamed per GPU per step",
                    "kernel_id": kernel_id, "flags": args.flags},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "worst_case": worst, "tolerance_mode": tol,
+        "single_frame_launches": single,
         "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
