@@ -18,6 +18,7 @@
 // Exactness of everything else: fp32 chains from -guard, truncation compared at +guard, exact double
 // re-evaluation (full_TB.h:58-63 / :71-75) when they differ.  MODE 1 = LANCZOS_FLAG_TOLERANCE_1LSB (V pass plain fp32).
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -429,17 +430,16 @@ int launch_dyn_one(const KParams &k, const FastHostTables &t, cudaStream_t s) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     auto kern = lanczos_dyn_kernel<C, A, N, D, MODE>;
     const size_t smem = sizeof(SmemD<G>) + 128;
-    static bool attr_set[64] = {};
-    static int ctas_per_sm[64] = {};
-    if (!attr_set[dev & 63]) {
+    // per device, set once; the calls are idempotent, so two threads racing here only repeat them
+    static std::atomic<int> ctas_per_sm[64] = {};
+    if (ctas_per_sm[dev & 63].load(std::memory_order_acquire) == 0) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32, smem) != cudaSuccess || nb < 1) nb = 8;
-        ctas_per_sm[dev & 63] = nb;
-        attr_set[dev & 63] = true;
+        ctas_per_sm[dev & 63].store(nb, std::memory_order_release);
     }
     // vertical segments: (waves) x (rows per segment + warm-up), as in lanczos_v6.cu
-    const long long slots = (long long)ctas_per_sm[dev & 63] * sms;
+    const long long slots = (long long)ctas_per_sm[dev & 63].load(std::memory_order_relaxed) * sms;
     const long long cols = (long long)strips * k.n_frames;
     const int max_segs = std::max(1, vperiods / std::max(1, (2 * G::RB) / D));
     int segs = 1;

@@ -26,6 +26,7 @@
 // filter of plan.cpp and recomputed exactly when it fails.  Recomputations are deferred to
 // per-CTA lists so that they run 32 lanes wide.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <type_traits>
@@ -503,10 +504,10 @@ int launch_one(const KParams &k, const FastHostTables &t, cudaStream_t s) {
 
     auto kern = lanczos_fast_kernel<C, A, N, D, PH, KM, NT>;
     const size_t smem = sizeof(FastSmem<G>) + 128;
-    static bool attr_set[64] = {};
-    if (!attr_set[dev & 63]) {
+    static std::atomic<bool> attr_set[64] = {};     // per device; the call is idempotent, a race only repeats it
+    if (!attr_set[dev & 63].load(std::memory_order_acquire)) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        attr_set[dev & 63] = true;
+        attr_set[dev & 63].store(true, std::memory_order_release);
     }
     dim3 grid(strips, segs, k.n_frames);
     kern<<<grid, NT, smem, s>>>(map, p);

@@ -29,6 +29,7 @@
 // MODE 1 (LANCZOS_FLAG_TOLERANCE_1LSB): the V pass is plain fp32 (no guard, no phase-0 test); the H pass
 // stays exact, so every output byte is within 1 LSB of the reference.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -894,16 +895,15 @@ int launch_v6_one(const KParams &k, const FastHostTables &t, int *alias_in_kerne
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     auto kern = lanczos_v6_kernel<C, A, N, D, PH, KM, W, MODE, ST64>;
     const size_t smem = W * sizeof(Smem6<G>) + 128;
-    static bool attr_set[64] = {};
-    static int ctas_per_sm[64] = {};
-    if (!attr_set[dev & 63]) {
+    // per device, set once; the calls are idempotent, so two threads racing here only repeat them
+    static std::atomic<int> ctas_per_sm[64] = {};
+    if (ctas_per_sm[dev & 63].load(std::memory_order_acquire) == 0) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32 * W, smem) != cudaSuccess || nb < 1) nb = 4;
-        ctas_per_sm[dev & 63] = nb;
-        attr_set[dev & 63] = true;
+        ctas_per_sm[dev & 63].store(nb, std::memory_order_release);
     }
-    const long long slots = (long long)ctas_per_sm[dev & 63] * sms * W;      // resident warps = strips in flight
+    const long long slots = (long long)ctas_per_sm[dev & 63].load(std::memory_order_relaxed) * sms * W;      // resident warps = strips in flight
     const long long cols = (long long)strips * k.n_frames;
     const int max_segs = std::max(1, vperiods / std::max(1, (2 * G::RB) / D));
     int segs = 1;

@@ -362,3 +362,36 @@ def test_planar_batch_of_frames(torch_cuda, lz, oracle):
     got = d_out.cpu().numpy()
     for i in range(f):
         assert np.array_equal(got[i], oracle.expected_planar(imgs[i], 192, 108, 3, 2, 1, fast=True))
+
+
+def test_concurrent_host_threads(torch_cuda, lz, oracle):
+    """The library is re-entrant (the reference is single-shot: globals lanczos.cpp:17-18, static pos :54): four host
+    threads, each with its own stream and its own descriptors, get the reference's pixels."""
+    import threading
+    jobs = [(96, 54, 2, 1, 3, 3), (64, 48, 3, 2, 3, 4), (100, 60, 17, 10, 3, 3), (240, 97, 2, 1, 3, 3)]
+    results, errors = {}, []
+
+    def worker(idx):
+        try:
+            iw, ih, n, d, a, c = jobs[idx]
+            ow, oh = oracle.out_dims(iw, ih, n, d)
+            st = torch_cuda.cuda.Stream()
+            for rep in range(6):
+                img = noise_hwc(oracle, ih, iw, c, seed=100 * idx + rep)
+                with torch_cuda.cuda.stream(st):
+                    d_in = torch_cuda.from_numpy(img).cuda()
+                    d_out = torch_cuda.empty((oh, ow, c), dtype=torch_cuda.uint8, device="cuda")
+                    lz.upscale_device(d_in, d_out, a=a, scale_n=n, scale_d=d)
+                st.synchronize()
+                results[(idx, rep)] = (d_out.cpu().numpy(), img, (ow, oh, a, n, d))
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(len(jobs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for (idx, rep), (got, img, (ow, oh, a, n, d)) in results.items():
+        assert np.array_equal(got, oracle.upscale(img, ow, oh, a, n, d)), (idx, rep)
