@@ -501,12 +501,13 @@ int lanczos_b200_upscale_hls(const lanczos_desc *desc, const uint8_t *d_in, uint
     if (out_frame_stride == 0) out_frame_stride = r.out_pitch * r.out_h;
     g_stats = lanczos_stats{};
     if (n_frames == 0) return LANCZOS_OK;
+    int kid = 100;
     cudaError_t e = (cudaError_t)launch_hls(d_in, d_out, r.in_pitch, r.out_pitch, in_frame_stride, out_frame_stride,
                                             n_frames, r.in_w, r.in_h, r.out_w, r.out_h, r.channels, r.a, r.scale_n,
-                                            bit_precision, lut, (cudaStream_t)cuda_stream);
+                                            bit_precision, lut, &kid, (cudaStream_t)cuda_stream);
     if (e != cudaSuccess) return cuda_fail(e, "launch_hls");
     g_stats.kernel_launches = 1;
-    g_stats.kernel_id = 100;
+    g_stats.kernel_id = kid;
     return LANCZOS_OK;
 }
 

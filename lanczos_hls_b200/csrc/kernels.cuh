@@ -50,9 +50,10 @@ int launch_dyn(const KParams &p, const FastHostTables &t, int *kernel_id, cudaSt
 // In-place top rows (full_TB.h:67-77 aliasing), exact double arithmetic.
 int launch_alias_rows(const KParams &p, cudaStream_t s);
 // Fixed-point HLS arithmetic (lanczos_hls.cu), integer scales; lut has a*n+1 entries in units of 2^-bp.
+// *kernel_id: 101 = tiled kernel (a, n compile-time, bp = 8), 100 = generic tile kernel.
 int launch_hls(const uint8_t *in, uint8_t *out, long long in_pitch, long long out_pitch, long long in_fs,
                long long out_fs, int n_frames, int in_w, int in_h, int out_w, int out_h, int channels, int a, int n,
-               int bp, const int *lut, cudaStream_t s);
+               int bp, const int *lut, int *kernel_id, cudaStream_t s);
 // Packed 24-bit words <-> interleaved RGB for lanczos_b200_stream.
 int launch_words_to_rgb(const uint32_t *words, uint8_t *rgb, long long n_px, cudaStream_t s);
 int launch_rgb_to_words(const uint8_t *rgb, uint32_t *words, long long n_px, cudaStream_t s);
