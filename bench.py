@@ -505,6 +505,8 @@ def main():
             lz.upscale(h_in, OUT_W, OUT_H, a=A, scale_n=SN, scale_d=SD, flags=args.flags, device=local_rank, out=h_out)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        if os.environ.get("LZB_BENCH_DEBUG"):
+            print(f"[rank {rank}] e2e dt {dt * 1e3 / e_steps:.2f} ms per step", file=sys.stderr, flush=True)
         te = torch.tensor([dt], dtype=torch.float64, device=dev)
         if dist is not None:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
