@@ -215,7 +215,15 @@ lanczos_dyn_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
     // ------------------------------ per-lane H geometry (fixed for the strip) ------------------------------
     const bool active = VB * lane < valid_bytes;
     int off[4];                 // byte offset of tap 0 in a staged row
-    float wq[4][TAPS];          // phase weights (times 2^24) of the lane's 4 samples
+    // A byte loaded with LDS.U8 sits in the low bits of a register: read as fp32 that is the DENORMAL b * 2^-149,
+    // and FFMA takes denormal operands at full rate.  With weights times 2^100 the chain runs in units of 2^-49
+    // pixels: every intermediate is the same mantissa as in pixel units with the exponent shifted (nothing
+    // underflows: the smallest term is ~2^-62), so after one exact multiplication by 2^49 the sum has the very
+    // bits of the PRMT/FHADD formulation used elsewhere -- and the per-tap conversion instruction is gone.
+    constexpr float kDenScale = 7.555786372591432e22f;    // 2^76: wtab already carries 2^24
+    constexpr float kDenUnscale = 5.62949953421312e14f;  // 2^49
+    constexpr float kDenGuard = 1.7763568394002505e-15f; // 2^-49
+    float wq[4][TAPS];          // phase weights (times 2^100) of the lane's 4 samples
     uint32_t p0mask = 0;        // byte lanes (0xff each) that hold phase-0 samples
 #pragma unroll
     for (int e = 0; e < 4; e++) {
@@ -224,7 +232,7 @@ lanczos_dyn_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
         const int ph = (xx * D) % N;
         off[e] = p.i0x[xx] * C + c - xbyte0;
 #pragma unroll
-        for (int k = 0; k < TAPS; k++) wq[e][k] = p.wtab[ph * 8 + k];
+        for (int k = 0; k < TAPS; k++) wq[e][k] = p.wtab[ph * 8 + k] * kDenScale;   // exact: a power of two
         if (ph == 0) p0mask |= 0xffu << (8 * e);
     }
     // phase-0 byte columns of the strip: pixels xx = N*m, all channels;
@@ -254,11 +262,11 @@ lanczos_dyn_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
                 float xa[4];
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
-                    float acc = -guard;
+                    float acc = -guard * kDenGuard;
 #pragma unroll
                     for (int k = 0; k < TAPS; k++)
-                        acc = fmaf(h2_lo_to_f32((uint32_t)row[off[e] + k * C]), wq[e][k], acc);
-                    xa[e] = acc;
+                        acc = fmaf(__uint_as_float((uint32_t)row[off[e] + k * C]), wq[e][k], acc);
+                    xa[e] = acc * kDenUnscale;
                 }
                 const uint32_t qa = quantise4(xa[0], xa[1], xa[2], xa[3]);
                 const uint32_t qb = quantise4(xa[0] + g2, xa[1] + g2, xa[2] + g2, xa[3] + g2);
