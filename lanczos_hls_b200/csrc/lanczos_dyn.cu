@@ -93,6 +93,13 @@ template <int N, int D> __host__ __device__ constexpr int cntmaxd() {
     return best;
 }
 
+// fma.rn.f32 WITHOUT .ftz whatever the compilation flags say (-use_fast_math would flush the denormal operand)
+__device__ __forceinline__ float fma_keep_denormals(float a, float b, float c) {
+    float d;
+    asm("fma.rn.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
 template <class G>
 struct __align__(128) SmemD {             // one per warp
     uint8_t in[G::STAGES][G::STAGE_B];    // TMA destinations, row lr at lr * BOX_B
@@ -265,7 +272,7 @@ lanczos_dyn_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
                     float acc = -guard * kDenGuard;
 #pragma unroll
                     for (int k = 0; k < TAPS; k++)
-                        acc = fmaf(__uint_as_float((uint32_t)row[off[e] + k * C]), wq[e][k], acc);
+                        acc = fma_keep_denormals(__uint_as_float((uint32_t)row[off[e] + k * C]), wq[e][k], acc);
                     xa[e] = acc * kDenUnscale;
                 }
                 const uint32_t qa = quantise4(xa[0], xa[1], xa[2], xa[3]);
