@@ -42,6 +42,8 @@ struct DynParams {
     const int32_t *i0x;       // [out_w] first tap pixel per output pixel (plan AxisTables)
     const double *wdx, *wdy;  // per-coordinate double weights (exact evaluation)
     float guard;              // rigorous fp32 error bound (x1.06) of ascending-order chains with the phase table
+    int p0_filter;            // 1: phase-0 coordinates are exactly integral and the residues have the a = 3 pattern,
+                              //    so the "cannot flip" test of lanczos_v6.cu (K = 3/8) decides most phase-0 samples
     float wtab[32 * 8];       // polyphase table [N][8] (padded to 8 taps), times 2^24
     unsigned long long *strict_counter;
 };
@@ -91,6 +93,12 @@ template <int N, int D> __host__ __device__ constexpr int cntmaxd() {
     int best = 1;
     for (int s = 0; s < D; s++) best = cntd<N, D>(s) > best ? cntd<N, D>(s) : best;
     return best;
+}
+
+__device__ __forceinline__ uint32_t hfma2_d(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
 }
 
 // fma.rn.f32 WITHOUT .ftz whatever the compilation flags say (-use_fast_math would flush the denormal operand)
@@ -301,6 +309,15 @@ lanczos_dyn_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
             if (ob < 0) continue;
             const int xx = ob / C, c = ob - xx * C;
             const uint8_t *tap0 = &sm.in[st][lr * G::BOX_B] + (p.i0x[xx] * C + c - xbyte0);
+            if (p.p0_filter) {
+                // the reference returns the centre value v unless the negative residues at +-2 pixels outweigh half
+                // the spacing of doubles below v (plan.cpp): 3 b <= 8 v on both sides proves that they do not
+                const int v = tap0[(A - 1) * C], b0 = tap0[(A - 3) * C], b4 = tap0[(A + 1) * C];
+                if (3 * max(b0, b4) <= 8 * v) {
+                    sm.ring[slot0 + lr][ob - obyte0] = (uint8_t)v;
+                    continue;
+                }
+            }
             sm.ring[slot0 + lr][ob - obyte0] = exact_taps<TAPS>(tap0, C, [&](int k) { return p.wdx[(long long)xx * TAPS + k]; });
             n_strict++;
         }
@@ -376,10 +393,27 @@ lanczos_dyn_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
                             bool doubt = false;
                             if (ph == 0) {
                                 // phase 0: start from the centre tap; the reference's value is that or one less, v_fix_dyn decides
-                                const uint8_t *crow = vit + (u - A) * SWB;
-                                if (u - A < 0 && it * G::U + u - A < 0) crow += wrapoff;
-                                qv = *reinterpret_cast<const uint32_t *>(crow);
+                                auto ring_row = [&](int o) {              // ring row `o` rows from this iteration's first
+                                    const uint8_t *r = vit + o * SWB;
+                                    if (o < 0 && it * G::U + o < 0) r += wrapoff;
+                                    return *reinterpret_cast<const uint32_t *>(r);
+                                };
+                                qv = ring_row(u - A);
                                 doubt = true;
+                                if (A == 3 && p.p0_filter) {
+                                    // v - 0.375 b >= 0 for the rows 2 above and 2 below the centre, as in lanczos_v6.cu:
+                                    // one fp16 FMA per test on the raw fp16-subnormal bytes, the sign is exact
+                                    const uint32_t wa = ring_row(u - A - 2), wb = ring_row(u - A + 2);
+                                    const uint32_t kR = 0xB600B600u;      // -0.375
+                                    uint32_t z = 0;
+#pragma unroll
+                                    for (int hsel = 0; hsel < 2; hsel++) {
+                                        const uint32_t sel = hsel ? 0x4342u : 0x4140u;
+                                        const uint32_t hv = __byte_perm(qv, 0u, sel);
+                                        z |= hfma2_d(__byte_perm(wa, 0u, sel), kR, hv) | hfma2_d(__byte_perm(wb, 0u, sel), kR, hv);
+                                    }
+                                    doubt = (z & 0x80008000u) != 0u;
+                                }
                             } else {
                                 qv = quantise4(res[q][0], res[q][1], res[q][2], res[q][3]);
                                 if (MODE == 0) {
@@ -489,6 +523,17 @@ int launch_dyn_one(const KParams &k, const FastHostTables &t, cudaStream_t s) {
     p.seg_periods = seg_periods; p.vperiod0 = vperiod0;
     p.i0x = k.i0x; p.wdx = k.wdx; p.wdy = k.wdy;
     p.guard = k.guard_asc;
+    // the cheap phase-0 test needs: coordinates exactly integral in double on both axes (then the weights there are
+    // the whole-pixel residues for every coordinate), a = 3 with negative residues exactly at +-2 pixels, K <= 3/8
+    {
+        int km = 0;
+        bool small = true;
+        for (int q = 0; q < 2 * A; q++) {
+            if (t.align_k[q] != 0.f) km |= 1 << q;
+            if (t.align_k[q] > 0.374f) small = false;
+        }
+        p.p0_filter = (A == 3 && km == 0x11 && small && t.exact_x && t.exact_y) ? 1 : 0;
+    }
     for (int ph = 0; ph < N; ph++)
         for (int q = 0; q < 8; q++) p.wtab[ph * 8 + q] = q < 2 * A ? t.phase_w[ph * 2 * A + q] * 16777216.f : 0.f;
     p.strict_counter = k.strict_counter;
