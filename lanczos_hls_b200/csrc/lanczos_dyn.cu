@@ -261,6 +261,23 @@ lanczos_dyn_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
         return (ob >= obyte0 && ob < obyte0 + valid_bytes) ? ob : -1;
     };
     constexpr int P0Q = (SWB / (N * C) + 2) * C;              // candidate columns to scan
+    // after the row loop lane l takes the (column, row) pairs t = l, l + 32, ...: the same pairs in every chunk, so
+    // what each needs is packed into one register now -- row << 20 | strip byte column << 12 | tap-0 byte offset
+    // in the staged row -- or -1 when the candidate column lies outside the strip
+    constexpr int P0_ITEMS = (P0Q * RB + 31) / 32;
+    static_assert(G::BOX_B < 4096 && SWB <= 256 && RB < 2048, "packing of the phase-0 work items");
+    int p0_item[P0_ITEMS];
+#pragma unroll
+    for (int i = 0; i < P0_ITEMS; i++) {
+        const int t = lane + 32 * i;
+        const int q = t / RB, lr = t - q * RB;
+        const int ob = (t < P0Q * RB) ? p0_column(q) : -1;
+        p0_item[i] = -1;
+        if (ob >= 0) {
+            const int xx = ob / C, c = ob - xx * C;
+            p0_item[i] = (lr << 20) | ((ob - obyte0) << 12) | (p.i0x[xx] * C + c - xbyte0);
+        }
+    }
 
     int n_strict = 0;
     const float guard = p.guard, g2 = 2.f * p.guard;
@@ -301,24 +318,24 @@ lanczos_dyn_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
             }
         }
         __syncwarp();   // the words written above are patched byte-wise by other lanes now
-        // phase-0 samples: fixed byte columns of the strip, every row, always exact; one (column, row) per lane
-#pragma unroll 1
-        for (int t = lane; t < P0Q * RB; t += 32) {
-            const int q = t / RB, lr = t - q * RB;
-            const int ob = p0_column(q);
-            if (ob < 0) continue;
-            const int xx = ob / C, c = ob - xx * C;
-            const uint8_t *tap0 = &sm.in[st][lr * G::BOX_B] + (p.i0x[xx] * C + c - xbyte0);
+        // phase-0 samples: fixed byte columns of the strip, every row; one (column, row) per lane and round
+#pragma unroll
+        for (int i = 0; i < P0_ITEMS; i++) {
+            const int it = p0_item[i];
+            if (it < 0) continue;
+            const int lr = it >> 20, col = (it >> 12) & 0xff;
+            const uint8_t *tap0 = &sm.in[st][lr * G::BOX_B] + (it & 0xfff);
             if (p.p0_filter) {
                 // the reference returns the centre value v unless the negative residues at +-2 pixels outweigh half
                 // the spacing of doubles below v (plan.cpp): 3 b <= 8 v on both sides proves that they do not
                 const int v = tap0[(A - 1) * C], b0 = tap0[(A - 3) * C], b4 = tap0[(A + 1) * C];
                 if (3 * max(b0, b4) <= 8 * v) {
-                    sm.ring[slot0 + lr][ob - obyte0] = (uint8_t)v;
+                    sm.ring[slot0 + lr][col] = (uint8_t)v;
                     continue;
                 }
             }
-            sm.ring[slot0 + lr][ob - obyte0] = exact_taps<TAPS>(tap0, C, [&](int k) { return p.wdx[(long long)xx * TAPS + k]; });
+            const int xx = (obyte0 + col) / C;
+            sm.ring[slot0 + lr][col] = exact_taps<TAPS>(tap0, C, [&](int k) { return p.wdx[(long long)xx * TAPS + k]; });
             n_strict++;
         }
     };
