@@ -250,6 +250,24 @@ lanczos_dyn_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
         for (int k = 0; k < TAPS; k++) wq[e][k] = p.wtab[ph * 8 + k] * kDenScale;   // exact: a power of two
         if (ph == 0) p0mask |= 0xffu << (8 * e);
     }
+    // C = 3: the lane's fourth byte is the channel of its first byte one pixel on, and its taps start 0 or 1 pixel
+    // later (upscaling), i.e. they are six of the seven bytes off[0] + 3k, k = 0..6.  Its weights are spread over
+    // those seven positions (a zero at the unused end: fma(t, 0, acc) == acc, same bits) and its six loads are gone.
+    constexpr bool SHARE = (C == 3);
+    float w3s[TAPS + 1];
+#pragma unroll
+    for (int k = 0; k <= TAPS; k++) w3s[k] = 0.f;
+    if (SHARE) {
+        const int d3 = (off[3] - off[0]) / C;      // 0 or 1 for every lane that owns columns
+#pragma unroll
+        for (int k = 0; k <= TAPS; k++) {
+            const int src = k - d3;
+            float w = 0.f;
+#pragma unroll
+            for (int j = 0; j < TAPS; j++) w = (src == j) ? wq[3][j] : w;
+            w3s[k] = w;
+        }
+    }
     // phase-0 byte columns of the strip: pixels xx = N*m, all channels;
     // enumerate them on the fly: column index q -> output byte column (or -1)
     auto p0_column = [&](int q) -> int {
@@ -292,8 +310,20 @@ lanczos_dyn_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
             for (int lr = 0; lr < RB; lr++) {
                 const uint8_t *row = &sm.in[st][lr * G::BOX_B];
                 float xa[4];
+                if (SHARE) {
+                    float t[TAPS + 1];
 #pragma unroll
-                for (int e = 0; e < 4; e++) {
+                    for (int k = 0; k <= TAPS; k++) t[k] = __uint_as_float((uint32_t)row[off[0] + k * C]);
+                    float a0 = -guard * kDenGuard, a3 = a0;
+#pragma unroll
+                    for (int k = 0; k < TAPS; k++) a0 = fma_keep_denormals(t[k], wq[0][k], a0);
+#pragma unroll
+                    for (int k = 0; k <= TAPS; k++) a3 = fma_keep_denormals(t[k], w3s[k], a3);
+                    xa[0] = a0 * kDenUnscale;
+                    xa[3] = a3 * kDenUnscale;
+                }
+#pragma unroll
+                for (int e = SHARE ? 1 : 0; e < (SHARE ? 3 : 4); e++) {
                     float acc = -guard * kDenGuard;
 #pragma unroll
                     for (int k = 0; k < TAPS; k++)
