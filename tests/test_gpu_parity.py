@@ -395,3 +395,18 @@ def test_concurrent_host_threads(torch_cuda, lz, oracle):
     assert not errors, errors
     for (idx, rep), (got, img, (ow, oh, a, n, d)) in results.items():
         assert np.array_equal(got, oracle.upscale(img, ow, oh, a, n, d)), (idx, rep)
+
+
+def test_planar_pitched_planes(torch_cuda, lz, oracle):
+    """Planes with a row pitch larger than the width and planes that are not adjacent in memory."""
+    c, ih, iw = 3, 54, 96
+    img = planar(noise_hwc(oracle, ih, iw, c, seed=9))
+    want = oracle.expected_planar(img, 192, 108, 3, 2, 1, fast=True)
+    big_in = torch_cuda.zeros((c, ih + 3, iw + 32), dtype=torch_cuda.uint8, device="cuda")
+    big_out = torch_cuda.full((c, 108 + 5, 192 + 64), 7, dtype=torch_cuda.uint8, device="cuda")
+    big_in[:, :ih, :iw] = torch_cuda.from_numpy(img).cuda()
+    lz.upscale_planar_device(big_in[:, :ih, :iw], big_out[:, :108, :192], a=3)
+    torch_cuda.cuda.synchronize()
+    got = big_out.cpu().numpy()
+    assert np.array_equal(got[:, :108, :192], want)
+    assert (got[:, 108:, :] == 7).all() and (got[:, :, 192:] == 7).all()      # nothing outside the planes is touched
