@@ -410,3 +410,34 @@ def test_planar_pitched_planes(torch_cuda, lz, oracle):
     got = big_out.cpu().numpy()
     assert np.array_equal(got[:, :108, :192], want)
     assert (got[:, 108:, :] == 7).all() and (got[:, :, 192:] == 7).all()      # nothing outside the planes is touched
+
+
+@pytest.mark.parametrize("cfg", [  # in_w, in_h, n, d, a, c: one shape per specialised kernel family
+    (240, 97, 2, 1, 3, 3), (124, 70, 3, 2, 3, 4), (240, 120, 17, 10, 3, 3), (96, 54, 3, 1, 3, 3), (37, 23, 2, 1, 3, 4),
+])
+def test_nothing_is_written_outside_the_output_rectangle(torch_cuda, lz, oracle, cfg):
+    """Canary bytes around a pitched output (and below its last row) survive every kernel family."""
+    iw, ih, n, d, a, c = cfg
+    ow, oh = oracle.out_dims(iw, ih, n, d)
+    img = noise_hwc(oracle, ih, iw, c, seed=3)
+    pad = 64                                             # keeps pitch and base aligned for the specialised kernels
+    big = torch_cuda.full((oh + 4, ow * c + pad), 0xA5, dtype=torch_cuda.uint8, device="cuda")
+    d_out = big[:oh].as_strided((oh, ow, c), (ow * c + pad, c, 1))
+    d_in = torch_cuda.from_numpy(img).cuda()
+    lz.upscale_device(d_in, d_out, a=a, scale_n=n, scale_d=d)
+    torch_cuda.cuda.synchronize()
+    got = big.cpu().numpy()
+    assert np.array_equal(got[:oh, :ow * c].reshape(oh, ow, c), oracle.upscale(img, ow, oh, a, n, d))
+    assert (got[:oh, ow * c:] == 0xA5).all() and (got[oh:] == 0xA5).all()
+
+
+def test_hls_mode_writes_only_its_output(lz, oracle):
+    import torch
+    img = noise_hwc(oracle, 50, 167, 3, seed=5)
+    big = torch.full((100 + 3, 334 * 3 + 32), 0x5A, dtype=torch.uint8, device="cuda")
+    d_out = big[:100].as_strided((100, 334, 3), (334 * 3 + 32, 3, 1))
+    lz.upscale_hls_device(torch.from_numpy(img).cuda(), d_out)
+    torch.cuda.synchronize()
+    got = big.cpu().numpy()
+    assert np.array_equal(got[:100, :334 * 3].reshape(100, 334, 3), oracle.hls_upscale(img, 2))
+    assert (got[:100, 334 * 3:] == 0x5A).all() and (got[100:] == 0x5A).all()
