@@ -1,5 +1,6 @@
 """Randomised differential test: CUDA path (C ABI) vs the CPU oracle on many small random shapes, ratios,
-contents and layouts.  usage: python tools/fuzz_parity.py [seconds] [seed]   (needs a GPU; exits 1 on a mismatch)"""
+contents and layouts.  usage: [FUZZ_MAXW=300 FUZZ_MAXH=120] python tools/fuzz_parity.py [seconds] [seed]
+(needs a GPU; exits 1 on a mismatch)"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -10,13 +11,14 @@ from util import noise_hwc, smooth_hwc, dark_hwc, planar
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 12345)
+MAXW, MAXH = int(os.environ.get("FUZZ_MAXW", "300")), int(os.environ.get("FUZZ_MAXH", "120"))
 RATIOS = [(2, 1), (2, 1), (3, 2), (17, 10), (3, 1), (5, 3), (4, 1), (1, 1), (7, 4)]
 t0, n, kernels = time.time(), 0, {}
 while time.time() - t0 < budget:
     nn, dd = RATIOS[rng.integers(len(RATIOS))]
     a = int(rng.choice([3, 3, 3, 2, 1, 4]))
     c = int(rng.choice([3, 3, 4, 1, 2]))
-    iw = int(rng.integers(2 * a + 1, 300)); ih = int(rng.integers(2 * a + 1, 120))
+    iw = int(rng.integers(2 * a + 1, MAXW)); ih = int(rng.integers(2 * a + 1, MAXH))
     if rng.random() < 0.6:                       # shapes the specialised kernels accept
         iw = max(16, iw // 16 * 16)
     ow, oh = O.out_dims(iw, ih, nn, dd)
