@@ -48,6 +48,9 @@
 #ifndef LZB_MINB
 #define LZB_MINB 16      // resident warps per SM the register allocation aims for
 #endif
+#ifndef LZB_TOL_VU
+#define LZB_TOL_VU 1     // ratio periods per V loop iteration in MODE 1 at D = 1 (2: +2 % on 1080p, -5 % on 4K)
+#endif
 #ifndef LZB_W
 #define LZB_W 1          // independent warps (strips) per CTA
 #endif
@@ -493,9 +496,6 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
     constexpr bool FILTER = (MODE == 0) && (KM != 0);
     // input rows per V loop iteration: one (even) ratio period.  LZB_TOL_VU = 2 lets the plain fp32 V pass of MODE 1
     // take two of them at D = 1: +2 % on 1080p batches, -5 % on 4K ones (measured), so it stays off.
-#ifndef LZB_TOL_VU
-#define LZB_TOL_VU 1
-#endif
     constexpr int VU = (MODE == 1 && D == 1 && G::RB % (LZB_TOL_VU * G::U) == 0) ? LZB_TOL_VU * G::U : G::U;
     static_assert(KM == 0 || (A == 3 && KM == 0x11), "phase-0 row filter is written for the +-2 residues of a = 3");
     extern __shared__ __align__(128) uint8_t smem_raw[];
