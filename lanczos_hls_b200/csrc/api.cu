@@ -5,6 +5,7 @@
 // Here that is per-GPU CUDA streams with chunked host<->device copies overlapping the kernels,
 // frame batches or row bands as the unit of work, and no collectives.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -27,7 +28,7 @@ namespace {
 
 thread_local std::string g_last_cuda_error;
 thread_local lanczos_stats g_stats{};
-bool g_stats_enabled = false;
+std::atomic<bool> g_stats_enabled{false};
 
 int cuda_fail(cudaError_t e, const char *what) {
     g_last_cuda_error = std::string(what) + ": " + cudaGetErrorString(e);
@@ -51,9 +52,88 @@ struct DeviceGuard {
     }
 };
 
+// Non-blocking streams of the host drivers, kept per device between calls (creating and destroying a stream
+// costs tens of microseconds).  A lease synchronises its stream before handing it back, on every exit path,
+// so no copy or kernel is still running on a scratch buffer when the buffer returns to its pool.
+std::mutex g_stream_mutex;
+std::map<int, std::vector<cudaStream_t>> g_idle_streams;
+struct StreamLease {
+    int device = -1;
+    cudaStream_t s = nullptr;
+    cudaError_t acquire(int dev) {
+        device = dev;
+        {
+            std::lock_guard<std::mutex> l(g_stream_mutex);
+            auto &v = g_idle_streams[dev];
+            if (!v.empty()) {
+                s = v.back();
+                v.pop_back();
+                return cudaSuccess;
+            }
+        }
+        return cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    }
+    cudaError_t sync() { return s ? cudaStreamSynchronize(s) : cudaSuccess; }
+    ~StreamLease() {
+        if (!s) return;
+        if (cudaStreamSynchronize(s) != cudaSuccess) {   // sticky error: do not reuse
+            cudaStreamDestroy(s);
+            return;
+        }
+        std::lock_guard<std::mutex> l(g_stream_mutex);
+        g_idle_streams[device].push_back(s);
+    }
+    StreamLease() = default;
+    StreamLease(const StreamLease &) = delete;
+    StreamLease &operator=(const StreamLease &) = delete;
+};
+
+// Row-pitched copies between a caller's host image (pitch = the caller's) and a device scratch image whose
+// pitch is the row size rounded up to 16 bytes (what the TMA kernels want).  Only the pixels of a row are
+// touched on either side: padding bytes of the caller's buffer are neither read nor written.
+long long scratch_pitch(long long row_bytes) { return (row_bytes + 15) / 16 * 16; }
+cudaError_t copy_rows(void *dst, long long dpitch, const void *src, long long spitch, long long row_bytes, long long rows,
+                      cudaMemcpyKind kind, cudaStream_t s) {
+    if (rows <= 0) return cudaSuccess;
+    if (dpitch == row_bytes && spitch == row_bytes) return cudaMemcpyAsync(dst, src, (size_t)(row_bytes * rows), kind, s);
+    return cudaMemcpy2DAsync(dst, (size_t)dpitch, src, (size_t)spitch, (size_t)row_bytes, (size_t)rows, kind, s);
+}
+
+// ---- host plans (tables only, no device memory), cached per geometry ---------------------------
+using HostKey = std::tuple<int, int, int, int, int, int, int, int, unsigned>;
+std::mutex g_host_plan_mutex;
+std::map<HostKey, std::shared_ptr<const Plan>> g_host_plans;
+constexpr unsigned kPlanFlagMask = LANCZOS_FLAG_NO_ALIAS;  // flags that change the tables
+
+int get_host_plan(const lanczos_desc *desc, std::shared_ptr<const Plan> *out) {
+    lanczos_desc r;
+    int rc = resolve_desc(desc, &r);
+    if (rc != LANCZOS_OK) return rc;
+    HostKey key{r.in_w, r.in_h, r.out_w, r.out_h, r.channels, r.a, r.scale_n, r.scale_d, r.flags & kPlanFlagMask};
+    {
+        std::lock_guard<std::mutex> lock(g_host_plan_mutex);
+        auto it = g_host_plans.find(key);
+        if (it != g_host_plans.end()) {
+            *out = it->second;
+            return LANCZOS_OK;
+        }
+    }
+    auto p = std::make_shared<Plan>();
+    rc = build_plan(&r, p.get());   // O(out_w + out_h) libm calls: outside the lock
+    if (rc != LANCZOS_OK) return rc;
+    // plans are shared by callers with different row pitches: nothing may read the pitches of the first caller
+    p->d.in_pitch = p->d.out_pitch = 0;
+    std::lock_guard<std::mutex> lock(g_host_plan_mutex);
+    auto ins = g_host_plans.emplace(key, p);
+    *out = ins.first->second;
+    return LANCZOS_OK;
+}
+
 // ---- device-resident plan -----------------------------------------------------------------
 struct DevicePlan {
-    Plan host;
+    std::shared_ptr<const Plan> host_ref;
+    const Plan &host() const { return *host_ref; }
+    std::mutex stats_mutex;   // the strict-sample counter is one per plan: calls that count take turns
     int device = 0;
     void *blob = nullptr;  // one allocation holding every table
     const int32_t *i0x = nullptr, *i0y = nullptr;
@@ -72,8 +152,6 @@ using PlanKey = std::tuple<int, int, int, int, int, int, int, int, unsigned, int
 std::mutex g_plan_mutex;
 std::map<PlanKey, std::shared_ptr<DevicePlan>> g_plans;
 
-constexpr unsigned kPlanFlagMask = LANCZOS_FLAG_NO_ALIAS;  // flags that change the tables
-
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int get_plan(const lanczos_desc *desc, int device, std::shared_ptr<DevicePlan> *out) {
@@ -90,9 +168,9 @@ int get_plan(const lanczos_desc *desc, int device, std::shared_ptr<DevicePlan> *
     }
     auto dp = std::make_shared<DevicePlan>();
     dp->device = device;
-    rc = build_plan(&r, &dp->host);
+    rc = get_host_plan(&r, &dp->host_ref);
     if (rc != LANCZOS_OK) return rc;
-    const Plan &h = dp->host;
+    const Plan &h = dp->host();
     // layout of the single device blob (each table 256-byte aligned)
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
@@ -172,7 +250,7 @@ struct Scratch {  // RAII device buffer from the pool (current device must be `d
 int run_device(const DevicePlan &dp, unsigned flags, const uint8_t *d_in, uint8_t *d_out, int n_frames,
                long long in_frame_stride, long long out_frame_stride, int out_row0, int out_rows,
                int in_row0, int in_rows, long long in_pitch, long long out_pitch, cudaStream_t s) {
-    const Plan &h = dp.host;
+    const Plan &h = dp.host();
     KParams p{};
     p.in = d_in;
     p.out = d_out;
@@ -193,23 +271,26 @@ int run_device(const DevicePlan &dp, unsigned flags, const uint8_t *d_in, uint8_
     p.guard_outer = h.guard_outer;
     p.alias_rows = h.alias_rows; p.alias_top_row = h.alias_top_row; p.alias_in_rows = h.alias_in_rows;
     p.flags = flags;
-    p.strict_counter = g_stats_enabled ? dp.strict_counter : nullptr;
+    const bool count = g_stats_enabled.load(std::memory_order_relaxed);
+    p.strict_counter = count ? dp.strict_counter : nullptr;
     g_stats = lanczos_stats{};
-    if (g_stats_enabled) CU(cudaMemsetAsync(dp.strict_counter, 0, 8, s));
     if (n_frames <= 0 || out_rows <= 0) return LANCZOS_OK;
+    // counting calls are synchronous and take turns on the plan's counter (several host threads or streams may share a plan)
+    std::unique_lock<std::mutex> stats_lock;
+    if (count) {
+        stats_lock = std::unique_lock<std::mutex>(const_cast<DevicePlan &>(dp).stats_mutex);
+        CU(cudaMemsetAsync(dp.strict_counter, 0, 8, s));
+    }
 
     int kid = 0, alias_done = 0;
     int frc = -1;
     if (!(flags & LANCZOS_FLAG_GENERIC_KERNEL)) {
         FastHostTables t{h.phase_w.data(), h.phase_wd.data(), h.align_k.data(), h.x.aligned_exact ? 1 : 0,
                          h.y.aligned_exact ? 1 : 0, h.x.uniform_phase ? 1 : 0, h.y.uniform_phase ? 1 : 0, h.x.i0.data(), h.p0_half2};
-        // development switch: LZB_IMPL=v5 selects the first-generation specialised kernels
-        const char *impl = getenv("LZB_IMPL");
-        if (!(impl && impl[0] == 'v' && impl[1] == '5')) frc = launch_v6(p, t, &kid, &alias_done, s);
-        if (frc < 0 && !(impl && impl[0] == 'v' && impl[1] == '5')) frc = launch_dyn(p, t, &kid, s);
-        if (frc < 0 && !(flags & LANCZOS_FLAG_TOLERANCE_1LSB)) frc = launch_fast(p, t, &kid, s);
+        frc = launch_v6(p, t, &kid, &alias_done, s);
+        if (frc < 0) frc = launch_dyn(p, t, &kid, s);
     }
-    if (frc > 0) return cuda_fail((cudaError_t)frc, "launch_fast");
+    if (frc > 0) return cuda_fail((cudaError_t)frc, "specialised kernel launch");
     cudaError_t e = cudaSuccess;
     if (frc < 0) {
         kid = 0;
@@ -226,7 +307,7 @@ int run_device(const DevicePlan &dp, unsigned flags, const uint8_t *d_in, uint8_
         g_stats.kernel_launches++;
         g_stats.alias_rows = std::min(h.alias_rows, out_row0 + out_rows) - out_row0;
     }
-    if (g_stats_enabled) {
+    if (count) {
         unsigned long long c = 0;
         CU(cudaMemcpyAsync(&c, dp.strict_counter, 8, cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
@@ -238,6 +319,8 @@ int run_device(const DevicePlan &dp, unsigned flags, const uint8_t *d_in, uint8_
 int check_band(const Plan &h, int out_row0, int out_rows, int in_row0, int in_rows) {
     if (out_row0 < 0 || out_rows < 0 || out_row0 + out_rows > h.d.out_h) return LANCZOS_ERR_BAND;
     if (out_rows == 0) return LANCZOS_OK;
+    // the supplied rows must be rows of the image: a kernel indexes them as (row - in_row0) * pitch
+    if (in_row0 < 0 || in_rows < 0 || in_row0 + in_rows > h.d.in_h) return LANCZOS_ERR_BAND;
     int need0, needn;
     band_rows(h, out_row0, out_rows, &need0, &needn);
     if (in_row0 > need0 || in_row0 + in_rows < need0 + needn) return LANCZOS_ERR_BAND;
@@ -272,7 +355,7 @@ const char *lanczos_b200_strerror(int code) {
 
 const char *lanczos_b200_last_cuda_error(void) { return g_last_cuda_error.c_str(); }
 
-void lanczos_b200_enable_stats(int on) { g_stats_enabled = on != 0; }
+void lanczos_b200_enable_stats(int on) { g_stats_enabled.store(on != 0, std::memory_order_relaxed); }
 
 int lanczos_b200_get_stats(lanczos_stats *out) {
     if (!out) return LANCZOS_ERR_NULL;
@@ -284,6 +367,10 @@ void lanczos_b200_clear_plans(void) {
     {
         std::lock_guard<std::mutex> lock(g_plan_mutex);
         g_plans.clear();
+    }
+    {
+        std::lock_guard<std::mutex> lock(g_host_plan_mutex);
+        g_host_plans.clear();
     }
     std::lock_guard<std::mutex> l(g_pool_mutex);
     for (auto &kv : g_pools) {
@@ -347,21 +434,21 @@ int lanczos_b200_phase0_constants(const lanczos_desc *desc, uint32_t *half2_cons
 
 int lanczos_b200_alias_rows(const lanczos_desc *desc) {
     if (!desc) return LANCZOS_ERR_NULL;
-    Plan p;
-    int rc = build_plan(desc, &p);
+    std::shared_ptr<const Plan> p;
+    int rc = get_host_plan(desc, &p);
     if (rc != LANCZOS_OK) return rc;
-    return p.alias_rows;
+    return p->alias_rows;
 }
 
 int lanczos_b200_band_input_rows(const lanczos_desc *desc, int32_t out_row0, int32_t out_rows,
                                  int32_t *in_row0, int32_t *in_rows) {
     if (!desc || !in_row0 || !in_rows) return LANCZOS_ERR_NULL;
-    Plan p;
-    int rc = build_plan(desc, &p);
+    std::shared_ptr<const Plan> p;
+    int rc = get_host_plan(desc, &p);
     if (rc != LANCZOS_OK) return rc;
-    if (out_row0 < 0 || out_rows < 1 || out_row0 + out_rows > p.d.out_h) return LANCZOS_ERR_BAND;
+    if (out_row0 < 0 || out_rows < 1 || out_row0 + out_rows > p->d.out_h) return LANCZOS_ERR_BAND;
     int a, b;
-    band_rows(p, out_row0, out_rows, &a, &b);
+    band_rows(*p, out_row0, out_rows, &a, &b);
     *in_row0 = a;
     *in_rows = b;
     return LANCZOS_OK;
@@ -424,7 +511,7 @@ int lanczos_b200_upscale_batch(const lanczos_desc *desc, const uint8_t *d_in, ui
     std::shared_ptr<DevicePlan> dp;
     int rc = get_plan(desc, device, &dp);
     if (rc != LANCZOS_OK) return rc;
-    const lanczos_desc &r = dp->host.d;
+    const lanczos_desc &r = dp->host().d;
     lanczos_desc user;
     resolve_desc(desc, &user);  // user pitches (plans are shared across pitches)
     if (in_frame_stride == 0) in_frame_stride = user.in_pitch * r.in_h;
@@ -459,7 +546,7 @@ int lanczos_b200_upscale_band(const lanczos_desc *desc, const uint8_t *d_in_band
     std::shared_ptr<DevicePlan> dp;
     int rc = get_plan(desc, device, &dp);
     if (rc != LANCZOS_OK) return rc;
-    rc = check_band(dp->host, out_row0, out_rows, in_row0, in_rows);
+    rc = check_band(dp->host(), out_row0, out_rows, in_row0, in_rows);
     if (rc != LANCZOS_OK) return rc;
     lanczos_desc user;
     resolve_desc(desc, &user);
@@ -523,12 +610,13 @@ int lanczos_b200_upscale_host(const lanczos_desc *desc, const uint8_t *h_in, uin
     std::shared_ptr<DevicePlan> dp;
     int rc = get_plan(desc, device, &dp);
     if (rc != LANCZOS_OK) return rc;
-    const Plan &h = dp->host;
+    const Plan &h = dp->host();
     lanczos_desc user;
     resolve_desc(desc, &user);
-    const long long in_frame = user.in_pitch * h.d.in_h, out_frame = user.out_pitch * h.d.out_h;
-    if (in_frame_stride == 0) in_frame_stride = in_frame;
-    if (out_frame_stride == 0) out_frame_stride = out_frame;
+    const long long in_row = (long long)h.d.in_w * h.d.channels, out_row = (long long)h.d.out_w * h.d.channels;
+    const long long d_in_pitch = scratch_pitch(in_row), d_out_pitch = scratch_pitch(out_row);
+    if (in_frame_stride == 0) in_frame_stride = user.in_pitch * h.d.in_h;
+    if (out_frame_stride == 0) out_frame_stride = user.out_pitch * h.d.out_h;
     if (n_streams < 1) n_streams = 3;
     n_streams = std::min(n_streams, 8);
 
@@ -551,39 +639,36 @@ int lanczos_b200_upscale_host(const lanczos_desc *desc, const uint8_t *h_in, uin
     }
     size_t max_in = 0, max_out = 0;
     for (auto &it : items) {
-        max_in = std::max(max_in, (size_t)(it.in_rows * user.in_pitch));
-        max_out = std::max(max_out, (size_t)(it.out_rows * user.out_pitch));
+        max_in = std::max(max_in, (size_t)(it.in_rows * d_in_pitch));
+        max_out = std::max(max_out, (size_t)(it.out_rows * d_out_pitch));
     }
     n_streams = std::max(1, std::min<int>(n_streams, (int)items.size()));
-    std::vector<cudaStream_t> streams(n_streams);
+    // declaration order matters: the leases are destroyed (= synchronised) before the scratch buffers are released
     std::vector<std::unique_ptr<Scratch>> bin(n_streams), bout(n_streams);
+    std::vector<StreamLease> streams(n_streams);
     for (int i = 0; i < n_streams; i++) {
-        CU(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking));
+        CU(streams[i].acquire(device));
         bin[i].reset(new Scratch(device, max_in));
         bout[i].reset(new Scratch(device, max_out));
         if (!bin[i]->p || !bout[i]->p) return LANCZOS_ERR_NOMEM;
     }
     int64_t launches = 0;
-    rc = LANCZOS_OK;
-    for (size_t k = 0; k < items.size() && rc == LANCZOS_OK; k++) {
+    for (size_t k = 0; k < items.size(); k++) {
         const Item &it = items[k];
-        const int s = (int)(k % n_streams);
+        const int si = (int)(k % n_streams);
+        cudaStream_t s = streams[si].s;
         const uint8_t *src = h_in + it.frame * in_frame_stride + (long long)it.in_row0 * user.in_pitch;
         uint8_t *dst = h_out + it.frame * out_frame_stride + (long long)it.out_row0 * user.out_pitch;
-        CU(cudaMemcpyAsync(bin[s]->p, src, (size_t)it.in_rows * user.in_pitch, cudaMemcpyHostToDevice, streams[s]));
-        rc = run_device(*dp, desc->flags, (const uint8_t *)bin[s]->p, (uint8_t *)bout[s]->p, 1, 0, 0,
-                        it.out_row0, it.out_rows, it.in_row0, it.in_rows, user.in_pitch, user.out_pitch, streams[s]);
+        CU(copy_rows(bin[si]->p, d_in_pitch, src, user.in_pitch, in_row, it.in_rows, cudaMemcpyHostToDevice, s));
+        rc = run_device(*dp, desc->flags, (const uint8_t *)bin[si]->p, (uint8_t *)bout[si]->p, 1, 0, 0,
+                        it.out_row0, it.out_rows, it.in_row0, it.in_rows, d_in_pitch, d_out_pitch, s);
         launches += g_stats.kernel_launches;
-        if (rc != LANCZOS_OK) break;
-        CU(cudaMemcpyAsync(dst, bout[s]->p, (size_t)it.out_rows * user.out_pitch, cudaMemcpyDeviceToHost, streams[s]));
+        if (rc != LANCZOS_OK) return rc;
+        CU(copy_rows(dst, user.out_pitch, bout[si]->p, d_out_pitch, out_row, it.out_rows, cudaMemcpyDeviceToHost, s));
     }
-    for (int i = 0; i < n_streams; i++) {
-        cudaError_t e = cudaStreamSynchronize(streams[i]);
-        if (e != cudaSuccess && rc == LANCZOS_OK) rc = cuda_fail(e, "cudaStreamSynchronize");
-        cudaStreamDestroy(streams[i]);
-    }
+    for (int i = 0; i < n_streams; i++) CU(streams[i].sync());
     g_stats.kernel_launches = launches;
-    return rc;
+    return LANCZOS_OK;
 }
 
 int lanczos_b200_upscale_host_bands(const lanczos_desc *desc, const uint8_t *h_in, uint8_t *h_out,
@@ -593,6 +678,8 @@ int lanczos_b200_upscale_host_bands(const lanczos_desc *desc, const uint8_t *h_i
     lanczos_desc user;
     int rc = resolve_desc(desc, &user);
     if (rc != LANCZOS_OK) return rc;
+    const long long in_row = (long long)user.in_w * user.channels, out_row = (long long)user.out_w * user.channels;
+    const long long d_in_pitch = scratch_pitch(in_row), d_out_pitch = scratch_pitch(out_row);
     std::vector<int> rcs(n_devices, LANCZOS_OK);
     std::vector<std::string> errs(n_devices);
     std::vector<int64_t> launches(n_devices, 0);
@@ -610,23 +697,21 @@ int lanczos_b200_upscale_host_bands(const lanczos_desc *desc, const uint8_t *h_i
                 int rc2 = get_plan(desc, dev, &dp);
                 if (rc2 != LANCZOS_OK) return rc2;
                 int in0, inn;
-                band_rows(dp->host, r0, r1 - r0, &in0, &inn);
-                Scratch bin(dev, (size_t)inn * user.in_pitch), bout(dev, (size_t)(r1 - r0) * user.out_pitch);
+                band_rows(dp->host(), r0, r1 - r0, &in0, &inn);
+                Scratch bin(dev, (size_t)(inn * d_in_pitch)), bout(dev, (size_t)((r1 - r0) * d_out_pitch));
                 if (!bin.p || !bout.p) return LANCZOS_ERR_NOMEM;
-                cudaStream_t s;
-                CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-                CU(cudaMemcpyAsync(bin.p, h_in + (long long)in0 * user.in_pitch, (size_t)inn * user.in_pitch,
-                                   cudaMemcpyHostToDevice, s));
+                StreamLease st;   // after the scratch buffers: synchronised before they are released
+                CU(st.acquire(dev));
+                CU(copy_rows(bin.p, d_in_pitch, h_in + (long long)in0 * user.in_pitch, user.in_pitch, in_row, inn,
+                             cudaMemcpyHostToDevice, st.s));
                 rc2 = run_device(*dp, desc->flags, (const uint8_t *)bin.p, (uint8_t *)bout.p, 1, 0, 0, r0,
-                                 r1 - r0, in0, inn, user.in_pitch, user.out_pitch, s);
+                                 r1 - r0, in0, inn, d_in_pitch, d_out_pitch, st.s);
                 launches[gidx] = g_stats.kernel_launches;
-                if (rc2 == LANCZOS_OK)
-                    CU(cudaMemcpyAsync(h_out + (long long)r0 * user.out_pitch, bout.p,
-                                       (size_t)(r1 - r0) * user.out_pitch, cudaMemcpyDeviceToHost, s));
-                cudaError_t e = cudaStreamSynchronize(s);
-                cudaStreamDestroy(s);
-                if (e != cudaSuccess && rc2 == LANCZOS_OK) return cuda_fail(e, "cudaStreamSynchronize");
-                return rc2;
+                if (rc2 != LANCZOS_OK) return rc2;
+                CU(copy_rows(h_out + (long long)r0 * user.out_pitch, user.out_pitch, bout.p, d_out_pitch, out_row, r1 - r0,
+                             cudaMemcpyDeviceToHost, st.s));
+                CU(st.sync());
+                return LANCZOS_OK;
             };
             rcs[gidx] = body();
             errs[gidx] = g_last_cuda_error;
@@ -654,17 +739,21 @@ int lanczos_b200_expected(const lanczos_desc *desc, const uint8_t *h_in_planar, 
     if (rc != LANCZOS_OK) return rc;
     DeviceGuard g(device);
     if (!g.ok) return cuda_fail(cudaErrorInvalidDevice, "cudaSetDevice");
-    // planes stay planes: each one is upscaled as a one-channel frame (no interleaving round trip)
-    d.in_pitch = d.out_pitch = 0;
-    const size_t in_bytes = (size_t)r.in_w * r.in_h * r.channels, out_bytes = (size_t)r.out_w * r.out_h * r.channels;
-    Scratch pin(device, in_bytes), pout(device, out_bytes);
+    // planes stay planes: each one is upscaled as a one-channel frame (no interleaving round trip); on the device
+    // the rows of a plane are padded to 16 bytes so that odd widths keep the TMA kernels
+    const long long planes = r.channels;
+    const long long d_in_pitch = scratch_pitch(r.in_w), d_out_pitch = scratch_pitch(r.out_w);
+    d.in_pitch = d_in_pitch;
+    d.out_pitch = d_out_pitch;
+    Scratch pin(device, (size_t)(d_in_pitch * r.in_h * planes)), pout(device, (size_t)(d_out_pitch * r.out_h * planes));
     if (!pin.p || !pout.p) return LANCZOS_ERR_NOMEM;
-    cudaStream_t s = nullptr;
-    CU(cudaMemcpyAsync(pin.p, h_in_planar, in_bytes, cudaMemcpyHostToDevice, s));
-    rc = lanczos_b200_upscale_planar(&d, (const uint8_t *)pin.p, (uint8_t *)pout.p, 1, 0, 0, device, s);
+    StreamLease st;
+    CU(st.acquire(device));
+    CU(copy_rows(pin.p, d_in_pitch, h_in_planar, r.in_w, r.in_w, (long long)r.in_h * planes, cudaMemcpyHostToDevice, st.s));
+    rc = lanczos_b200_upscale_planar(&d, (const uint8_t *)pin.p, (uint8_t *)pout.p, 1, 0, 0, device, st.s);
     if (rc != LANCZOS_OK) return rc;
-    CU(cudaMemcpyAsync(h_out_planar, pout.p, out_bytes, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
+    CU(copy_rows(h_out_planar, r.out_w, pout.p, d_out_pitch, r.out_w, (long long)r.out_h * planes, cudaMemcpyDeviceToHost, st.s));
+    CU(st.sync());
     return LANCZOS_OK;
 }
 
@@ -672,26 +761,28 @@ int lanczos_b200_stream(const lanczos_desc *desc, const uint32_t *h_in_words, ui
     if (!desc || !h_in_words || !h_out_words) return LANCZOS_ERR_NULL;
     if (desc->channels != 3) return LANCZOS_ERR_ALIGN;
     lanczos_desc d = *desc;
-    d.in_pitch = d.out_pitch = 0;
+    d.in_pitch = d.out_pitch = 0;   // a stream has no row padding (lanczos.cpp:56-62)
     DeviceGuard g(device);
     if (!g.ok) return cuda_fail(cudaErrorInvalidDevice, "cudaSetDevice");
     std::shared_ptr<DevicePlan> dp;
     int rc = get_plan(&d, device, &dp);
     if (rc != LANCZOS_OK) return rc;
-    const lanczos_desc &r = dp->host.d;
+    lanczos_desc r;
+    resolve_desc(&d, &r);           // dense pitches of THIS call: cached plans carry none
     const long long n_in = (long long)r.in_w * r.in_h, n_out = (long long)r.out_w * r.out_h;
     Scratch win(device, n_in * 4), iin(device, n_in * 3), iout(device, n_out * 3), wout(device, n_out * 4);
     if (!win.p || !iin.p || !iout.p || !wout.p) return LANCZOS_ERR_NOMEM;
-    cudaStream_t s = nullptr;
-    CU(cudaMemcpyAsync(win.p, h_in_words, n_in * 4, cudaMemcpyHostToDevice, s));
-    CU((cudaError_t)launch_words_to_rgb((const uint32_t *)win.p, (uint8_t *)iin.p, n_in, s));
+    StreamLease st;
+    CU(st.acquire(device));
+    CU(cudaMemcpyAsync(win.p, h_in_words, n_in * 4, cudaMemcpyHostToDevice, st.s));
+    CU((cudaError_t)launch_words_to_rgb((const uint32_t *)win.p, (uint8_t *)iin.p, n_in, st.s));
     rc = run_device(*dp, d.flags, (const uint8_t *)iin.p, (uint8_t *)iout.p, 1, 0, 0, 0, r.out_h, 0, r.in_h,
-                    r.in_pitch, r.out_pitch, s);
+                    r.in_pitch, r.out_pitch, st.s);
     if (rc != LANCZOS_OK) return rc;
     const int64_t launches = g_stats.kernel_launches + 2;
-    CU((cudaError_t)launch_rgb_to_words((const uint8_t *)iout.p, (uint32_t *)wout.p, n_out, s));
-    CU(cudaMemcpyAsync(h_out_words, wout.p, n_out * 4, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
+    CU((cudaError_t)launch_rgb_to_words((const uint8_t *)iout.p, (uint32_t *)wout.p, n_out, st.s));
+    CU(cudaMemcpyAsync(h_out_words, wout.p, n_out * 4, cudaMemcpyDeviceToHost, st.s));
+    CU(st.sync());
     g_stats.kernel_launches = launches;
     return LANCZOS_OK;
 }

@@ -1,5 +1,5 @@
 // fast_common.cuh -- device/host helpers shared by the TMA + register-window kernels
-// (lanczos_fast.cu: static-phase H pass for a few ratios; lanczos_dyn.cu: any ratio with N <= 32).
+// (lanczos_v6.cu: static-phase H pass for a few ratios; lanczos_dyn.cu: any ratio with N <= 32).
 #pragma once
 #include <cstdint>
 #include <cuda.h>

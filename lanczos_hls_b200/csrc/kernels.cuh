@@ -30,8 +30,8 @@ struct KParams {
 
 // Generic kernel: any ratio, any a<=4, channels 1..4. Returns cudaError_t as int.
 int launch_generic(const KParams &p, cudaStream_t s);
-// Specialised TMA + register-window kernels (lanczos_fast.cu). Returns 0 when launched, a positive
-// cudaError_t on failure, -1 when no specialisation applies (the caller then uses the generic kernel).
+// Specialised TMA + register-window kernels (lanczos_v6.cu, lanczos_dyn.cu). Their launchers return 0 when
+// launched, a positive cudaError_t on failure, -1 when no specialisation applies (the caller then falls back).
 struct FastHostTables {            // host-side views of the plan the specialised kernels need
     const float *phase_w;          // [N][2a]
     const double *phase_wd;        // [N][2a]
@@ -41,8 +41,7 @@ struct FastHostTables {            // host-side views of the plan the specialise
     const int32_t *i0x_host;       // [out_w] host copy of AxisTables.i0 (x axis)
     const uint32_t *p0_half2;      // [4] Plan.p0_half2
 };
-int launch_fast(const KParams &p, const FastHostTables &t, int *kernel_id, cudaStream_t s);
-// Second generation of the same (lanczos_v6.cu): 8-byte V columns, PRMT-spliced copies, scalar constant-bank FFMA.
+// Static-phase kernels (lanczos_v6.cu): 8-byte V columns, PRMT-spliced copies, scalar constant-bank FFMA.
 // *alias_in_kernel = 1 when the kernel also produced the in-place top rows (no launch_alias_rows needed).
 int launch_v6(const KParams &p, const FastHostTables &t, int *kernel_id, int *alias_in_kernel, cudaStream_t s);
 // Any-ratio member of the second generation (lanczos_dyn.cu): dynamic-phase H pass, static systolic V pass.

@@ -529,7 +529,7 @@ int launch_dyn_one(const KParams &k, const FastHostTables &t, cudaStream_t s) {
     // per device, set once; the calls are idempotent, so two threads racing here only repeat them
     static std::atomic<int> ctas_per_sm[64] = {};
     if (ctas_per_sm[dev & 63].load(std::memory_order_acquire) == 0) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return -1; }   // clear the error state: the caller falls back to another kernel
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32, smem) != cudaSuccess || nb < 1) nb = 8;
         ctas_per_sm[dev & 63].store(nb, std::memory_order_release);

@@ -115,6 +115,56 @@ def test_pitched_buffers(torch_cuda, lz, oracle):
     assert (out[:, ow * c:] == 0xAB).all()   # padding untouched
 
 
+def test_stream_shim_after_a_pitched_call_on_the_same_geometry(torch_cuda, lz, oracle):
+    """Plans are cached per geometry and shared by callers with different row pitches: the packed-word shim
+    must run on its own dense buffers even when a padded call created the plan first."""
+    torch = torch_cuda
+    lz.lib().lanczos_b200_clear_plans()
+    ih, iw, ow, oh = 26, 40, 80, 52
+    img = noise_hwc(oracle, ih, iw, 3, seed=31)
+    want = oracle.upscale(img, ow, oh, 3, 2, 1)
+    in_pitch, out_pitch = iw * 3 + 40, ow * 3 + 16
+    buf_in = torch.zeros((ih, in_pitch), dtype=torch.uint8, device="cuda")
+    buf_in[:, : iw * 3] = torch.from_numpy(img.reshape(ih, iw * 3)).cuda()
+    buf_out = torch.zeros((oh, out_pitch), dtype=torch.uint8, device="cuda")
+    desc = lz.make_desc(iw, ih, ow, oh, 3, 3, 2, 1, in_pitch, out_pitch)
+    assert lz.lib().lanczos_b200_upscale(C.byref(desc), C.c_void_p(buf_in.data_ptr()), C.c_void_p(buf_out.data_ptr()), 0, None) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(buf_out.cpu().numpy()[:, : ow * 3].reshape(oh, ow, 3), want)
+    words = img[..., 0].astype(np.uint32) | (img[..., 1].astype(np.uint32) << 8) | (img[..., 2].astype(np.uint32) << 16)
+    out = lz.lanczos_stream(words, iw, ih, ow, oh).reshape(oh, ow)
+    got = np.stack([(out >> (8 * i)) & 0xFF for i in range(3)], axis=-1).astype(np.uint8)
+    assert np.array_equal(got, want)
+    # and the dense device entry point after the padded one
+    assert np.array_equal(gpu_upscale(torch, lz, img, ow, oh, 3, 2, 1), want)
+
+
+@pytest.mark.parametrize("cfg", [(50, 33, 2, 1, 3), (64, 40, 2, 1, 3), (44, 30, 3, 2, 4)])
+def test_host_api_pitched_buffers_keep_their_padding(torch_cuda, lz, oracle, cfg):
+    """lanczos_b200_upscale_host with padded host rows: pixels only are read and written."""
+    iw, ih, n, d, c = cfg
+    ow, oh = oracle.out_dims(iw, ih, n, d)
+    frames = 7
+    in_pitch, out_pitch = iw * c + 5, ow * c + 11
+    h_in = np.full((frames, ih, in_pitch), 0x5A, np.uint8)
+    imgs = [noise_hwc(oracle, ih, iw, c, seed=40 + f) for f in range(frames)]
+    for f in range(frames):
+        h_in[f, :, : iw * c] = imgs[f].reshape(ih, iw * c)
+    h_in = np.ascontiguousarray(h_in.reshape(-1)[: frames * ih * in_pitch - 5])      # last row ends with its pixels
+    h_out = np.full(frames * oh * out_pitch, 0xC3, np.uint8)
+    desc = lz.make_desc(iw, ih, ow, oh, c, 3, n, d, in_pitch, out_pitch)
+    for n_frames, streams in [(frames, 2), (1, 3)]:
+        h_out[:] = 0xC3
+        rc = lz.lib().lanczos_b200_upscale_host(C.byref(desc), h_in.ctypes.data_as(C.c_void_p), h_out.ctypes.data_as(C.c_void_p),
+                                                n_frames, 0, 0, 0, streams)
+        assert rc == 0
+        out = h_out.reshape(frames, oh, out_pitch)
+        for f in range(n_frames):
+            assert np.array_equal(out[f, :, : ow * c].reshape(oh, ow, c), oracle.upscale(imgs[f], ow, oh, 3, n, d)), f
+        assert (out[:, :, ow * c:] == 0xC3).all()
+        assert (out[n_frames:] == 0xC3).all()
+
+
 @pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
 @pytest.mark.parametrize("cfg", [(120, 90, 17, 10, 3, 3), (64, 64, 2, 1, 3, 3), (90, 64, 3, 2, 3, 4)])
 def test_row_bands_concatenate_to_full(torch_cuda, lz, oracle, cfg, world):
@@ -150,6 +200,11 @@ def test_band_argument_errors(torch_cuda, lz):
         lz.upscale_band_device(desc, d_in, d_out, 120, 16, 0, 10)
     assert e.value.code == -7
     assert lz.lib().lanczos_b200_upscale(C.byref(desc), None, None, 0, None) == -1
+    # supplied rows must be rows of the image: negative start, negative count, past the last row
+    for (r0, nr) in [(-2, 12), (0, -1), (60, 10)]:
+        with pytest.raises(lz.LanczosError) as e:
+            lz.upscale_band_device(desc, d_in, d_out, 0, 4, r0, nr)
+        assert e.value.code == -7
 
 
 def test_host_api_single_and_batch(torch_cuda, lz, oracle):
