@@ -39,11 +39,8 @@
 #include "../../include/lanczos_b200.h"
 #include "fast_common.cuh"
 
-#ifndef LZB_V_FFMA2
-#define LZB_V_FFMA2 1   // V-pass multiply-adds as FFMA2 over column pairs
-#endif
 #ifndef LZB_HROUNDS
-#define LZB_HROUNDS 2     // H rounds (of 32 / MAX_GROUPS rows) per chunk
+#define LZB_HROUNDS 2     // H rounds (of 32 / MAX_GROUPS = 5 rows) per chunk
 #endif
 #ifndef LZB_MINB
 #define LZB_MINB 16      // resident warps per SM the register allocation aims for
@@ -87,6 +84,7 @@ struct V6Params {
 __host__ __device__ constexpr int cdiv6(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ constexpr int cmax6(int a, int b) { return a > b ? a : b; }
 __host__ __device__ constexpr int lcm2(int d) { return d % 2 == 0 ? d : 2 * d; }
+__host__ __device__ constexpr int gcd6(int a, int b) { return b == 0 ? a : gcd6(b, a % b); }
 
 template <int C, int A, int N, int D, int PH, int W>
 struct Geo6 {
@@ -105,11 +103,18 @@ struct Geo6 {
     static constexpr int MIS = (PAD_L - HALO_L) % 8;              // window start inside its first 8-byte unit
     static constexpr int WIN0 = PAD_L - HALO_L - MIS;             // first 8-byte unit (byte offset) of group 0
     static constexpr int NW2 = (MIS + WIN_B + 7) / 8;             // 8-byte loads per H item
-    static constexpr int MAX_GROUPS = 32 / (OUT_B / VB);            // H items per row of a warp's strip (5 for 48-byte items)
-    static constexpr int SW_MAX = MAX_GROUPS * OUT_B;             // strip width = ring pitch in bytes (240)
+    // A warp's strip is SWV = 256 output bytes wide and starts at a multiple of 256: every row piece the V pass
+    // stores is two whole 128-byte lines.  (Strips of 5 H items = 240 bytes left every other 32-byte sector and
+    // every 128-byte line shared between two warps: tools/wbench.cu measures 4.0 TB/s for that store pattern on
+    // this part against 6.8 TB/s for 256-byte pieces, and the V pass alone was bound by it.)  H items are OUT_B
+    // bytes wide and aligned to OUT_B, so the H pass of a strip covers the MAX_GROUPS items that contain it.
+    static constexpr int SWV = 32 * VB;
+    static constexpr int VOFF_MAX = OUT_B - gcd6(SWV, OUT_B);     // largest offset of a strip inside its first H item
+    static constexpr int MAX_GROUPS = cdiv6(VOFF_MAX + SWV, OUT_B);   // H items per row of a warp's strip (6 for 48-byte items)
+    static constexpr int SW_MAX = MAX_GROUPS * OUT_B;             // ring pitch in bytes (288)
     // a TMA box must start on a 16-byte boundary of the row: strips whose input starts 8 bytes off get a box
     // that starts 8 bytes early (XSHIFT_MAX extra bytes per row)
-    static constexpr int XSHIFT_MAX = ((MAX_GROUPS * IN_B) % 16 != 0) ? 8 : 0;
+    static constexpr int XSHIFT_MAX = (IN_B % 16 != 0) ? 8 : 0;   // H items start at multiples of IN_B input bytes
     static constexpr int BOX_B = 16 * cdiv6(XSHIFT_MAX + cmax6(PAD_L + MAX_GROUPS * IN_B + HALO_R, WIN0 + (MAX_GROUPS - 1) * IN_B + 8 * NW2), 16);
     static constexpr int HB = 32 / MAX_GROUPS;                    // rows one round of H items covers (one item per lane)
     static constexpr int HROUNDS = LZB_HROUNDS;                   // H rounds per chunk
@@ -117,14 +122,18 @@ struct Geo6 {
     static constexpr int REGIONS = 2;                             // ring regions of RB rows: V(c) reads region c and the tail of c-1
     static constexpr int RING = REGIONS * RB;                     // intermediate rows kept in smem
     static constexpr int STAGE_B = 128 * ((RB * BOX_B + 127) / 128);  // TMA destinations must be 128-byte aligned
+#ifdef LZB_STAGES
+    static constexpr int STAGES = LZB_STAGES;
+#else
     static constexpr int STAGES = HROUNDS > 1 ? 3 : 4;            // TMA stages in flight
+#endif
     // the first row pushed by a segment is rs = D*pv0 - A + 1, so (row - A) mod D is static per chunk row
     static constexpr int S0 = (((1 - 2 * A) % D) + D) % D;
     static constexpr int U = lcm2(D);                             // rows per V loop iteration (even: filter delay line parity)
     static constexpr int YROWS = N * RB / D;                      // output rows completed per chunk
     static_assert(IN_B % 8 == 0, "H item input must be 8-byte aligned");
     static_assert(OUT_B % 16 == 0, "H item output must be 16-byte aligned");
-    static_assert(OUT_B % VB == 0 && HB * MAX_GROUPS <= 32 && SW_MAX / VB <= 32, "one H item per lane and round, one V column per lane");
+    static_assert(OUT_B % VB == 0 && HB * MAX_GROUPS <= 32 && HB >= 1, "one H item per lane and round, one V column per lane");
     static_assert(RB % U == 0, "chunk must be a whole number of V loop iterations");
     static_assert(TAPS - 1 <= RB, "tap rows must not reach further back than one ring region");
     static_assert(BOX_B / 4 <= 256, "TMA box too wide");
@@ -349,82 +358,166 @@ __device__ __noinline__ int h_fix(const V6Params &p, const HFixArgs a) {
     return n_strict;
 }
 
-struct VFixArgs {
-    const uint8_t *col;       // this thread's column in ring row 0
-    uint8_t *ocol;            // this thread's column in output row `ybase`
-    long long opitch;
-    int ybase, rs, nbytes;    // nbytes: bytes of the column inside the image
-    uint32_t rows;            // bit yy: output row ybase + yy
+// Shared-memory loads by 32-bit shared address: the slow paths are out of line, where a generic pointer
+// would turn every access into a generic LD.
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 lds_v2(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+    return v;
+}
+// bit 0 of byte e (e = 0..3) -> bit e
+__device__ __forceinline__ uint32_t lsb4_to_bits(uint32_t x) {
+    return (((x & 0x01010101u) * 0x01020408u) >> 24) & 0xfu;
+}
+
+// full_TB.h:71-75 for byte `col_e` of one output row: NT taps from consecutive ring rows starting at slot0
+template <int NT, int RING, int SWM, class W>
+__device__ __forceinline__ uint32_t exact_ring(uint32_t col_e, int slot0, W weight) {
+    double sum = 0.0;
+#pragma unroll
+    for (int k = 0; k < NT; k++) {
+        int sl = slot0 + k;
+        if (sl >= RING) sl -= RING;
+        const double v = __hiloint2double(0x43300000, (int)lds_u8(col_e + sl * SWM)) - 4503599627370496.0;
+        sum = __dadd_rn(sum, __dmul_rn(v, weight(k)));
+    }
+    return quantise_f64(sum);
+}
+
+// ---- V-pass slow path: one call per loop iteration in which some lane found something -------------------
+// The hot loop stores every row as it comes out of the fp32 pipeline and only collects, per row, what says
+// "look again": for an interpolated row the XOR of its two truncations (x - guard, x + guard; a byte in doubt
+// differs by one, so bit 0 of the byte is set), for a phase-0 row (copy of a centre row) the sign bits of the
+// fp16x2 "cannot flip" tests.  v_fix_iter then re-reads the row it stored, replaces the bytes in question by what
+// the reference's double arithmetic gives (full_TB.h:71-75), and stores it again (same lane, program order).
+template <int A, int N, int D, int VU, int S0> __host__ __device__ constexpr int viter_interp_rows() {
+    int n = 0;
+    for (int u = 0; u < VU; u++) n += cnt6<N, D>((S0 + u) % D);
+    return n;
+}
+template <int A, int N, int D, int VU, int S0> __host__ __device__ constexpr int viter_centre_rows() {
+    int n = 0;
+    for (int u = 0; u < VU; u++) n += ((S0 + u + A) % D == 0) ? 1 : 0;
+    return n;
+}
+template <int NI, int NZ>
+struct VIterFlags {
+    uint32_t dx[NI > 0 ? NI : 1], dy[NI > 0 ? NI : 1];   // interpolated rows of the iteration, in the order they complete
+    uint32_t zr[NZ > 0 ? NZ : 1];                         // phase-0 rows of the iteration
 };
 
-template <int A, int N, int D, int KM, int RING, int SWM, int VB>
-__device__ __noinline__ int v_fix(const V6Params &p, const VFixArgs a) {
+// bytes of an interpolated row: NT = 2a taps from ring slots slot0 .. (ascending rows = ascending taps)
+template <int A, int N, int D, int RING, int SWM>
+__device__ __forceinline__ int fix_interp_bytes(const V6Params &p, uint32_t col, int slot_r, int y, uint32_t need, uint2 &q) {
     constexpr int TAPS = 2 * A;
-    static_assert(VB == 8, "v_fix re-checks one 8-byte column");
-    int n_strict = 0;
+    const int ph = (y * D) % N;
+    int slot0 = slot_r - (TAPS - 1);
+    if (slot0 < 0) slot0 += RING;
+    int n = 0;
 #pragma unroll 1
-    for (uint32_t m = a.rows; m; m &= m - 1) {
-        const int yy = __ffs(m) - 1;
-        const int y = a.ybase + yy;
-        const int ph = (y * D) % N;
-        const int s0 = ((y * D) / N - A + 1 - a.rs) % RING;       // ring slot of the first tap row (full_TB.h:72)
-        uint8_t *orow = a.ocol + (long long)yy * a.opitch;
-        uint32_t need = 0;                                        // bit e: byte e must be evaluated exactly
-        if (ph != 0) {
-            // the hot path's fp32 chains again for all 8 bytes (ascending taps, same weights: same bits)
-            float acc[VB];
+    for (; need; need &= need - 1) {
+        const int e = __ffs(need) - 1;
+        uint32_t v;
+        if (p.uniform_y && N <= 8) v = exact_ring<TAPS, RING, SWM>(col + e, slot0, [&](int k) { return p.wdtab[ph * 8 + k]; });
+        else v = exact_ring<TAPS, RING, SWM>(col + e, slot0, [&](int k) { return p.wdy[(long long)y * TAPS + k]; });
+        const int sh = 8 * (e & 3);
+        if (e < 4) q.x = (q.x & ~(0xffu << sh)) | (v << sh);
+        else q.y = (q.y & ~(0xffu << sh)) | (v << sh);
+        n++;
+    }
+    return n;
+}
+
+// bytes of a phase-0 row (copy of ring row c): the sharper vectorised test (phase0_doubt2) on all 8 bytes, then the
+// reference's double sum for what is still in doubt.  Runs when row c + 2 has arrived, i.e. with taps 0..4 (rows
+// c-2 .. c+2) in the ring.  Tap 5 (row c + 3) is not needed: its weight is < 1e-25 (checked on the host, `pattern`
+// in plan.cpp), so for a centre v >= 1 it adds less than 2^-80 of the running sum (no change in double), and for
+// v = 0 the quantiser returns 0 whatever the sign of the residues (full_TB.h:29-37), which is the copy.
+template <int A, int N, int D, int KM, int RING, int SWM>
+__device__ __forceinline__ int fix_phase0_bytes(const V6Params &p, uint32_t col, int slot_c, int y, uint32_t vmask, uint2 &q) {
+    static_assert(A == 3 && KM == 0x11, "written for the +-2 residues of a = 3");
+    constexpr int TAPS = 2 * A;
+    int slot0 = slot_c - 2;
+    if (slot0 < 0) slot0 += RING;
+    uint32_t hx[5][4];
 #pragma unroll
-            for (int i = 0; i < VB; i++) acc[i] = -p.guard_v;
+    for (int k = 0; k < 5; k++) {
+        int sl = slot0 + k;
+        if (sl >= RING) sl -= RING;
+        const uint2 w = lds_v2(col + sl * SWM);
+        hx[k][0] = __byte_perm(w.x, 0u, 0x4140); hx[k][1] = __byte_perm(w.x, 0u, 0x4342);
+        hx[k][2] = __byte_perm(w.y, 0u, 0x4140); hx[k][3] = __byte_perm(w.y, 0u, 0x4342);
+    }
+    uint32_t dz[4];
 #pragma unroll
-            for (int k = 0; k < TAPS; k++) {
-                const uint2 w = *reinterpret_cast<const uint2 *>(a.col + ((s0 + k) % RING) * SWM);
-                float x[VB];
-                word_to_f32x4(w.x, x[0], x[1], x[2], x[3]);
-                word_to_f32x4(w.y, x[4], x[5], x[6], x[7]);
-                const float wk = p.wtab[ph * 8 + k];
+    for (int i = 0; i < 4; i++) dz[i] = phase0_doubt2(hx[0][i], hx[1][i], hx[2][i], hx[3][i], hx[4][i], p.p0_nk0, p.p0_k1, p.p0_k3, p.p0_nk4);
+    // sign bits (bits 15 / 31 of dz[i] = bytes 2i / 2i+1) -> bit 7 of byte e, then one bit per byte
+    const uint32_t lo = __byte_perm(dz[0], dz[1], 0x7531), hi = __byte_perm(dz[2], dz[3], 0x7531);
+    int n = 0;
+#pragma unroll 1
+    for (uint32_t need = (sign4_to_bits(lo) | (sign4_to_bits(hi) << 4)) & vmask; need; need &= need - 1) {
+        const int e = __ffs(need) - 1;
+        const int sh = 8 * (e & 3);
+        if (((((e < 4) ? q.x : q.y) >> sh) & 0xffu) == 0u) continue;       // v = 0: clamped to 0 either way
+        uint32_t v;
+        if (p.uniform_y && N <= 8) v = exact_ring<5, RING, SWM>(col + e, slot0, [&](int k) { return p.wdtab[k]; });
+        else v = exact_ring<5, RING, SWM>(col + e, slot0, [&](int k) { return p.wdy[(long long)y * TAPS + k]; });
+        if (e < 4) q.x = (q.x & ~(0xffu << sh)) | (v << sh);
+        else q.y = (q.y & ~(0xffu << sh)) | (v << sh);
+        n++;
+    }
+    return n;
+}
+
+// col: shared address of the lane's column in ring row 0; slot_it: ring slot of the iteration's first row; yit / op:
+// output row the iteration's period starts at and the lane's column in that row; zmask: 0x80008000, or 0 with
+// LANCZOS_FLAG_FAST_ALIGNED (phase-0 rows stay copies).  Returns the number of samples evaluated in double.
+template <int A, int N, int D, int KM, int VU, int S0, int RING, int SWM, bool ST64>
+__device__ __noinline__ int v_fix_iter(const V6Params &p, uint32_t col, int slot_it, int yit, uint8_t *op, long long opitch,
+                                       const VIterFlags<viter_interp_rows<A, N, D, VU, S0>(), viter_centre_rows<A, N, D, VU, S0>()> f,
+                                       uint32_t zmask, int nbytes, int ys, int ye) {
+    const uint32_t vmask = nbytes >= 8 ? 0xffu : ((1u << nbytes) - 1u);
+    int n = 0, qi = 0, zi = 0;
+    auto redo = [&](int yoff, auto fix) {
+        const int y = yit + yoff;
+        if (y < ys || y >= ye) return;                     // never stored (warm-up rows, rows of the next segment)
+        uint8_t *orow = op + (long long)yoff * opitch;
+        uint2 q;
+        if (ST64) q = *reinterpret_cast<const uint2 *>(orow);
+        else { q.x = *reinterpret_cast<const uint32_t *>(orow); q.y = nbytes > 4 ? *reinterpret_cast<const uint32_t *>(orow + 4) : 0u; }
+        n += fix(y, q);
+        if (ST64) *reinterpret_cast<uint2 *>(orow) = q;
+        else { *reinterpret_cast<uint32_t *>(orow) = q.x; if (nbytes > 4) *reinterpret_cast<uint32_t *>(orow + 4) = q.y; }
+    };
 #pragma unroll
-                for (int i = 0; i < VB; i++) acc[i] = fmaf(x[i], wk, acc[i]);
+    for (int u = 0; u < VU; u++) {
+        const int s0 = (S0 + u) % D, tq = (S0 + u) / D;
+        if ((s0 + A) % D == 0) {
+            if constexpr (KM != 0) {
+                if ((f.zr[zi] & zmask) != 0u) {
+                    int slot_c = slot_it + u - 2;
+                    if (slot_c < 0) slot_c += RING;
+                    redo(N * ((S0 + u + A - 2) / D), [&](int y, uint2 &q) { return fix_phase0_bytes<A, N, D, KM, RING, SWM>(p, col, slot_c, y, vmask, q); });
+                }
             }
-            const float g2 = 2.f * p.guard_v;
-            const uint32_t dx = quantise4(acc[0], acc[1], acc[2], acc[3]) ^ quantise4(acc[0] + g2, acc[1] + g2, acc[2] + g2, acc[3] + g2);
-            const uint32_t dy = quantise4(acc[4], acc[5], acc[6], acc[7]) ^ quantise4(acc[4] + g2, acc[5] + g2, acc[6] + g2, acc[7] + g2);
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                if ((dx >> (8 * e)) & 0xffu) need |= 1u << e;
-                if ((dy >> (8 * e)) & 0xffu) need |= 1u << (4 + e);
-            }
-        } else if (A == 3 && KM == 0x11) {
-            // all 8 bytes of the row at once (fp16x2): which of them can the reference have turned into v - 1?
-            uint32_t hx[5][4];
-#pragma unroll
-            for (int k = 0; k < 5; k++) {
-                const uint2 w = *reinterpret_cast<const uint2 *>(a.col + ((s0 + k) % RING) * SWM);
-                hx[k][0] = __byte_perm(w.x, 0u, 0x4140); hx[k][1] = __byte_perm(w.x, 0u, 0x4342);
-                hx[k][2] = __byte_perm(w.y, 0u, 0x4140); hx[k][3] = __byte_perm(w.y, 0u, 0x4342);
-            }
-            uint32_t dz[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) dz[i] = phase0_doubt2(hx[0][i], hx[1][i], hx[2][i], hx[3][i], hx[4][i], p.p0_nk0, p.p0_k1, p.p0_k3, p.p0_nk4);
-            // sign bits (bits 15 / 31 of dz[i] = bytes 2i / 2i+1) -> bit 7 of byte e, then one bit per byte
-            const uint32_t lo = __byte_perm(dz[0], dz[1], 0x7531), hi = __byte_perm(dz[2], dz[3], 0x7531);
-            need = sign4_to_bits(lo) | (sign4_to_bits(hi) << 4);
-        } else {
-            need = 0xffu;
+            zi++;
         }
-        need &= (a.nbytes >= VB) ? 0xffu : ((1u << a.nbytes) - 1u);
-#pragma unroll 1
-        for (; need; need &= need - 1) {
-            const int e = __ffs(need) - 1;
-            uint8_t taps_b[TAPS];
 #pragma unroll
-            for (int k = 0; k < TAPS; k++) taps_b[k] = a.col[((s0 + k) % RING) * SWM + e];
-            if (ph == 0 && (A == 3 && KM == 0x11 ? taps_b[A - 1] == 0 : phase0_safe<TAPS, KM>(taps_b, 1, p.align_ki))) continue;
-            if (p.uniform_y && N <= 8) orow[e] = exact_taps<TAPS>(taps_b, 1, [&](int k) { return p.wdtab[ph * 8 + k]; });
-            else orow[e] = exact_taps<TAPS>(taps_b, 1, [&](int k) { return p.wdy[(long long)y * TAPS + k]; });
-            n_strict++;
+        for (int yr = ylo6<N, D>(s0); yr < yhi6<N, D>(s0); yr++) {
+            if ((yr * D) % N == 0) continue;
+            if ((f.dx[qi] | f.dy[qi]) != 0u) {
+                const uint32_t need = (lsb4_to_bits(f.dx[qi]) | (lsb4_to_bits(f.dy[qi]) << 4)) & vmask;
+                redo(N * tq + yr, [&](int y, uint2 &q) { return fix_interp_bytes<A, N, D, RING, SWM>(p, col, slot_it + u, y, need, q); });
+            }
+            qi++;
         }
     }
-    return n_strict;
+    return n;
 }
 
 // The reference's column pass runs in place from the bottom row up (full_TB.h:67-77): output row yy reads rows
@@ -493,7 +586,11 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
     constexpr int CEN = A - 1;                                  // centre tap of a phase-0 sample
     constexpr int NSLOT = nslot6<N, D, TAPS>();
     constexpr int CNTMAX = cmax6(1, cmax6(cnt6<N, D>(0), cnt6<N, D>(D - 1)));   // D <= 2
+#ifdef LZB_ABL_NOVFILTER     // ablation builds (timing experiments only, results are wrong): see tools/ablate.sh
+    constexpr bool FILTER = false;
+#else
     constexpr bool FILTER = (MODE == 0) && (KM != 0);
+#endif
     // input rows per V loop iteration: one (even) ratio period.  LZB_TOL_VU = 2 lets the plain fp32 V pass of MODE 1
     // take two of them at D = 1: +2 % on 1080p batches, -5 % on 4K ones (measured), so it stays off.
     constexpr int VU = (MODE == 1 && D == 1 && G::RB % (LZB_TOL_VU * G::U) == 0) ? LZB_TOL_VU * G::U : G::U;
@@ -504,15 +601,18 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
     const int tid = threadIdx.x & 31, warp = threadIdx.x >> 5;
     Smem6<G> &sm = reinterpret_cast<Smem6<G> *>(smem_raw)[warp];
     const int strip = blockIdx.x * W + warp, seg = blockIdx.y, frame = blockIdx.z;
-    if (strip * p.sw >= p.out_w * C) return;
+    if (strip * G::SWV >= p.out_w * C) return;
     uint8_t *out_frame = p.out + (long long)frame * p.out_frame_stride;
 
     // horizontal extent
-    const int obyte0 = strip * p.sw;                          // first output byte column of the strip
+    const int vbyte0 = strip * G::SWV;                        // first output byte column of the strip (V pass, stores)
     const int row_bytes = p.out_w * C;
-    const int valid_bytes = min(p.sw, row_bytes - obyte0);    // > 0 by construction of the grid
-    const int groups = min(p.groups, (valid_bytes + G::OUT_B - 1) / G::OUT_B);
-    const int ibyte0 = (obyte0 / (N * C)) * (D * C);          // first input byte column of the strip
+    const int valid_bytes = min(G::SWV, row_bytes - vbyte0);  // > 0 by construction of the grid
+    const int obyte0 = (vbyte0 / G::OUT_B) * G::OUT_B;        // first output byte column of the H items that cover it
+    const int voff = vbyte0 - obyte0;                         // 0, 16 or 32 for 48-byte items
+    const int groups = min(G::MAX_GROUPS, (voff + valid_bytes + G::OUT_B - 1) / G::OUT_B);
+    const int hvalid = min(groups * G::OUT_B, row_bytes - obyte0);   // bytes of the H items inside the image
+    const int ibyte0 = (obyte0 / (N * C)) * (D * C);          // first input byte column of the H items
     const int xshift = (ibyte0 - G::PAD_L) & 15;              // 0 or 8: the TMA box starts that many bytes early
     // vertical extent: periods [pv0, pv1) -> output rows [N*pv0, N*pv1), clipped to the band
     const int pv0 = p.vperiod0 + seg * p.seg_periods;
@@ -578,50 +678,72 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
                 word_to_f32x4(w.y, f[8 * wi + 4], f[8 * wi + 5], f[8 * wi + 6], f[8 * wi + 7]);
             }
             // window byte k (k = 0 is HALO_L bytes left of the item's own input) = f[MIS + k] * 2^24
-            // interpolated samples, in output order, packed 4 per word
+            // interpolated samples in output order (sample s: period s / ((N-1)*C), then phase, then channel).
+            // Channels c and c + 1 (c even) of a pixel use the same weights and their window bytes are neighbours:
+            // they share one FFMA2 chain (one issue slot and 1.8 pipe cycles for two FMAs instead of 2 x 1.15, same
+            // rounding as two FFMAs).  A window byte is only ever the first or only ever the second element of such
+            // a pair, so the converted values sit in aligned register pairs without copies.
+            float xa[4 * G::ND], xb[4 * G::ND];
+#pragma unroll
+            for (int s = 0; s < 4 * G::ND; s++) {
+                if (s >= G::NI) { xa[s] = xb[s] = 0.f; continue; }
+                const int per = s / ((N - 1) * C), rem = s % ((N - 1) * C);
+                const int r = 1 + rem / C, c = rem % C;
+                const int ph = (r * D) % N;
+                const int base = G::MIS + (per * D + (r * D) / N) * C + c;   // f index of tap 0
+                if (c % 2 == 0 && c + 1 < C) {
+                    float2 acc = make_float2(-guard_h, -guard_h);
+#pragma unroll
+                    for (int i = 0; i < TAPS; i++) {
+                        const int k = tap_order6<TAPS>(i);
+                        acc = __ffma2_rn(make_float2(f[base + k * C], f[base + k * C + 1]), make_float2(p.wtab[ph * 8 + k], p.wtab[ph * 8 + k]), acc);
+                    }
+                    const float2 accb = __fadd2_rn(acc, make_float2(g2h, g2h));
+                    xa[s] = acc.x; xa[s + 1] = acc.y;
+                    xb[s] = accb.x; xb[s + 1] = accb.y;
+                } else if (c % 2 == 0) {
+                    float acc = -guard_h;
+#pragma unroll
+                    for (int i = 0; i < TAPS; i++) {
+                        const int k = tap_order6<TAPS>(i);
+                        acc = fmaf(f[base + k * C], p.wtab[ph * 8 + k], acc);
+                    }
+                    xa[s] = acc;
+                    xb[s] = acc + g2h;
+                }
+            }
 #pragma unroll
             for (int dw = 0; dw < G::ND; dw++) {
-                float xa[4], xb[4];
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    const int s = 4 * dw + e;
-                    if (s < G::NI) {
-                        const int per = s / ((N - 1) * C), rem = s % ((N - 1) * C);
-                        const int r = 1 + rem / C, c = rem % C;
-                        const int ph = (r * D) % N;
-                        const int base = (per * D + (r * D) / N) * C + c;   // window index of tap 0
-                        float acc = -guard_h;
-#pragma unroll
-                        for (int i = 0; i < TAPS; i++) {
-                            const int k = tap_order6<TAPS>(i);
-                            acc = fmaf(f[G::MIS + base + k * C], p.wtab[ph * 8 + k], acc);
-                        }
-                        xa[e] = acc;
-                        xb[e] = acc + g2h;
-                    } else {
-                        xa[e] = xb[e] = 0.f;
-                    }
-                }
-                const uint32_t qa = quantise4(xa[0], xa[1], xa[2], xa[3]);
-                const uint32_t qb = quantise4(xb[0], xb[1], xb[2], xb[3]);
+                const uint32_t qa = quantise4(xa[4 * dw], xa[4 * dw + 1], xa[4 * dw + 2], xa[4 * dw + 3]);
+                const uint32_t qb = quantise4(xb[4 * dw], xb[4 * dw + 1], xb[4 * dw + 2], xb[4 * dw + 3]);
                 srcw[2 * G::NW2 + dw] = qa;
                 if (qa != qb) fix_g |= 1u << dw;
             }
             // phase-0 samples are copies of the centre tap; "cannot flip" filter of plan.cpp:
             // v - sum K_k*b_k >= 0 over the negative residues -> the reference returns v as well
+#ifndef LZB_ABL_NOHFILTER
             if (KM != 0) {
 #pragma unroll
                 for (int per = 0; per < PH; per++)
 #pragma unroll
-                    for (int c = 0; c < C; c++) {
-                        const int base = per * D * C + c;
-                        float z = f[G::MIS + base + CEN * C];
+                    for (int c = 0; c < C; c += 2) {
+                        const int base = G::MIS + per * D * C + c;
+                        if (c + 1 < C) {
+                            float2 z = make_float2(f[base + CEN * C], f[base + CEN * C + 1]);
 #pragma unroll
-                        for (int k = 0; k < TAPS; k++)
-                            if ((KM >> k) & 1) z = fmaf(f[G::MIS + base + k * C], -p.align_k[k], z);
-                        zor |= __float_as_uint(z);
+                            for (int k = 0; k < TAPS; k++)
+                                if ((KM >> k) & 1) z = __ffma2_rn(make_float2(f[base + k * C], f[base + k * C + 1]), make_float2(-p.align_k[k], -p.align_k[k]), z);
+                            zor |= __float_as_uint(z.x) | __float_as_uint(z.y);
+                        } else {
+                            float z = f[base + CEN * C];
+#pragma unroll
+                            for (int k = 0; k < TAPS; k++)
+                                if ((KM >> k) & 1) z = fmaf(f[base + k * C], -p.align_k[k], z);
+                            zor |= __float_as_uint(z);
+                        }
                     }
             }
+#endif
             // splice copies (raw input bytes) and interpolated bytes into the output words
             uint8_t *drow = &sm.ring[slot0][dst_off];
             uint4 *dst = reinterpret_cast<uint4 *>(drow);
@@ -656,7 +778,7 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
                 HFixArgs a;
                 const int lr = item / groups, g = item - lr * groups;
                 a.in_row = &sm.in[st][lr * G::BOX_B + xshift]; a.ring_row = drow; a.gbyte0 = g * G::OUT_B;
-                a.obyte0 = obyte0; a.ibyte0 = ibyte0; a.valid_bytes = valid_bytes;
+                a.obyte0 = obyte0; a.ibyte0 = ibyte0; a.valid_bytes = hvalid;
                 a.fix_g = fix_g; a.fix_z = zor >> 31; a.guard = guard_h;
                 n_strict += h_fix<C, A, N, D, PH, KM, G::PAD_L>(p, a);
             }
@@ -670,41 +792,48 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
     for (int j = 0; j < NSLOT; j++)
 #pragma unroll
         for (int i = 0; i < VB; i++) acc[j][i] = 0.f;
-    // phase-0 filter delay line: fp16x2 words (bytes * 2^-24) of the phase-0 rows 2 rows back
+    // Delay line of the phase-0 centre rows: a phase-0 output row (copy of centre row c) is stored when row c + 2
+    // arrives, together with the verdict of the "cannot flip" test on both of its +-2 neighbours.
+    //   FILTER: zA = the centre rows as fp16x2 words (bytes * 2^-24), zP = sign bits of the test against row c - 2
+    //   else:   wP = the centre rows as packed bytes
     constexpr int ZD = (D == 1) ? 2 : 1;                       // D = 1: rows r-1 and r-2 are both centres
-    uint32_t zA[ZD][VB / 2];
+    uint32_t zA[ZD][VB / 2], zP[ZD];
+    uint2 wP[ZD];
 #pragma unroll
-    for (int j = 0; j < ZD; j++)
+    for (int j = 0; j < ZD; j++) {
 #pragma unroll
         for (int i = 0; i < VB / 2; i++) zA[j][i] = 0u;
+        zP[j] = 0u;
+        wP[j] = make_uint2(0u, 0u);
+    }
     const bool v_active = VB * tid < valid_bytes;
     const bool v_second = VB * tid + 4 < valid_bytes;          // second word of the column inside the image (only !ST64)
     const float guard_v = MODE == 0 ? p.guard_v : 0.f, g2v = 2.f * p.guard_v;
     const long long opitch = p.out_pitch;
-    const uint8_t *vcol = &sm.ring[0][VB * tid];               // this thread's column of the ring
+    const uint8_t *vcol = &sm.ring[0][voff + VB * tid];        // this thread's column of the ring
+    uint32_t vcol_s = smem_u32(vcol);                          // ... as a 32-bit shared address (what the V loop works with)
+    asm volatile("" : "+r"(vcol_s));
     const int t0_first = (rs - A - G::S0) / D;                 // exact division (also for negative values)
-    int ybase = N * t0_first;                                  // output row of bit 0 of `fixrows` for the current chunk
-    uint8_t *ocol = out_frame + obyte0 + VB * tid + (long long)(ybase - p.out_row0) * opitch;   // column in row ybase
-    unsigned long long fixrows = 0;                            // bit yy: look at output row ybase + yy again
+    int ybase = N * t0_first;                                  // output row that period t of the chunk's first iteration starts at
+    uint8_t *ocol = out_frame + vbyte0 + VB * tid + (long long)(ybase - p.out_row0) * opitch;   // column in row ybase
+
+    constexpr int NI_IT = viter_interp_rows<A, N, D, VU, G::S0>(), NZ_IT = viter_centre_rows<A, N, D, VU, G::S0>();
+    const uint32_t zmask = p.strict_v_identity ? 0x80008000u : 0u;   // LANCZOS_FLAG_FAST_ALIGNED: phase-0 rows stay plain copies
 
     auto v_pass = [&](int chunk) {
         const int bslot = (chunk % G::REGIONS) * G::RB;
         const uint8_t *vrow = vcol + bslot * SWM;
-        // the centre tap row of a phase-0 output lies A rows back: in the previous region for the first A rows
-        const int wrapoff = (bslot == 0) ? G::RING * SWM : 0;
-        const bool interior = (ybase >= ys) && (ybase + G::YROWS + N <= ye);
+        // rows [ybase, ybase + YROWS + N * (A + 2) / D] can be stored by this chunk
+        const bool interior = (ybase - N >= ys) && (ybase + G::YROWS + N * (A + 2) <= ye);
         auto body = [&](auto check_tag) {
             constexpr bool CHECK = decltype(check_tag)::value;
             const uint8_t *vit = vrow;                         // first row of the iteration
-            uint8_t *op = ocol + (long long)ylo6<N, D>(G::S0) * opitch;   // next output row (rows come out in order)
+            uint8_t *op = ocol;                                // output row yit of this lane's column
             int yit = ybase;
-            // centre rows of phase-0 outputs lie A rows back; for the first A rows of a chunk that is the previous region
-            int wrapseq[VU];
-#pragma unroll
-            for (int u = 0; u < VU; u++) wrapseq[u] = wrapoff;
 #pragma unroll 1
             for (int it = 0; it < G::RB / VU; it++) {
-                uint32_t fl = 0;                               // flags of this iteration, bit = row - yit
+                VIterFlags<NI_IT, NZ_IT> fl;                   // what says "look again" (MODE 0), see v_fix_iter
+                int qi = 0, zi = 0;
 #pragma unroll
                 for (int u = 0; u < VU; u++) {
                     const int s0 = (G::S0 + u) % D, tq = (G::S0 + u) / D;   // completing centre = D*(t + tq) + s0
@@ -713,8 +842,13 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
                     const uint32_t h0 = __byte_perm(w.x, 0u, 0x4140), h1 = __byte_perm(w.x, 0u, 0x4342);
                     const uint32_t h2 = __byte_perm(w.y, 0u, 0x4140), h3 = __byte_perm(w.y, 0u, 0x4342);
                     float x[VB];
+#ifdef LZB_ABL_NOCONV           // ablation: no byte -> fp32 conversion
+                    x[0] = __uint_as_float(h0); x[1] = __uint_as_float(h0 + 1); x[2] = __uint_as_float(h1); x[3] = __uint_as_float(h1 + 1);
+                    x[4] = __uint_as_float(h2); x[5] = __uint_as_float(h2 + 1); x[6] = __uint_as_float(h3); x[7] = __uint_as_float(h3 + 1);
+#else
                     x[0] = h2_lo_to_f32(h0); x[1] = h2_hi_to_f32(h0); x[2] = h2_lo_to_f32(h1); x[3] = h2_hi_to_f32(h1);
                     x[4] = h2_lo_to_f32(h2); x[5] = h2_hi_to_f32(h2); x[6] = h2_lo_to_f32(h3); x[7] = h2_hi_to_f32(h3);
+#endif
                     // ---- systolic step: every pending output row takes its next tap from this row ----
                     float res[CNTMAX][VB];
                     {
@@ -727,7 +861,10 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
                             for (int yr = ylo6<N, D>(sdc); yr < yhi6<N, D>(sdc); yr++) {
                                 const int ph = (yr * D) % N;
                                 if (ph == 0) continue;
-#if LZB_V_FFMA2
+#ifdef LZB_ABL_TAPS             // ablation: only the first and the last LZB_ABL_TAPS/2 taps are computed
+                                if (dc >= LZB_ABL_TAPS / 2 && dc < TAPS - LZB_ABL_TAPS / 2) { q++; continue; }
+#endif
+#ifndef LZB_V_SCALAR
                                 // two columns per FFMA2 (one issue slot for two FMAs; same rounding as two FFMAs)
                                 const float2 wk2 = make_float2(p.wtab[ph * 8 + k], p.wtab[ph * 8 + k]);
 #pragma unroll
@@ -751,120 +888,119 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
                             }
                         }
                     }
-                    // ---- phase-0 "cannot flip" test on the fp16x2 pipe ----
-                    // this row r is a phase-0 centre iff (s0 + A) % D == 0; with b = bytes * 2^-24 (fp16 subnormals):
-                    //   zpost(r-2) = v[r-2] - 0.375*b[r]  and  zpre(r) = v[r] - 0.375*b[r-2]   (times 2^-24)
-                    //   One FMA each: the exact value (a multiple of 2^-27) is rounded once, to a multiple of 2^-24, and
-                    //   rounding never changes the sign (negative values round to a negative number or to -0).
-                    //   K = 3/8 >= plan.cpp's K_k: sign bit set means "may flip".  The delay line keeps the raw rows.
-                    if (FILTER && (s0 + A) % D == 0) {
-                        const int zs = (ZD == 2) ? (u & 1) : 0;       // D = 1: slot of row r-2 = slot this row overwrites
-                        const uint32_t kR = 0xB600B600u;              // -0.375
-                        const uint32_t hn[4] = {h0, h1, h2, h3};
-                        uint32_t zpost = 0, zpre = 0;
-#pragma unroll
-                        for (int i = 0; i < VB / 2; i++) {
-                            zpost |= hfma2_u(hn[i], kR, zA[zs][i]);
-                            zpre |= hfma2_u(zA[zs][i], kR, hn[i]);
-                            zA[zs][i] = hn[i];
+                    auto store_row = [&](int yoff, const uint2 qv) {
+#ifdef LZB_ABL_NOSTORE
+                        if (qv.x != 0x12345678u) return;
+#endif
+                        if (CHECK && (yit + yoff < ys || yit + yoff >= ye)) return;
+                        uint8_t *orow = op + (long long)yoff * opitch;
+                        if (ST64) {
+                            *reinterpret_cast<uint2 *>(orow) = qv;
+                        } else {
+                            *reinterpret_cast<uint32_t *>(orow) = qv.x;
+                            if (v_second) *reinterpret_cast<uint32_t *>(orow + 4) = qv.y;
                         }
-                        // output rows of centre r-2 = c+A-2 and of centre r = c+A, relative to yit (static)
-                        if (zpost & 0x80008000u) fl |= 1u << (N * (G::S0 + u + A - 2) / D);
-                        if (zpre & 0x80008000u) fl |= 1u << (N * (G::S0 + u + A) / D);
+                    };
+                    // ---- this row r is a phase-0 centre: the phase-0 output row of centre r - 2 goes out now ----
+                    // (rows r - 2 and r + 2 of a centre are centres themselves: D <= 2).  With b = bytes * 2^-24
+                    // (fp16 subnormals) and v the centre, one FMA per side and byte pair on the fp16x2 pipe:
+                    //   v[r-2] - 0.375*b[r]  (this row is the +2 neighbour)  and  v[r] - 0.375*b[r-2]  (kept in zP
+                    //   until row r + 2 arrives).  The exact value (a multiple of 2^-27) is rounded once, to a multiple
+                    //   of 2^-24, and rounding never changes the sign; 0.375 >= plan.cpp's K_k: a set sign bit means
+                    //   "the reference may return v - 1" (v_fix_iter looks again).
+                    if ((s0 + A) % D == 0) {
+                        const int zs = (ZD == 2) ? (u & 1) : 0;       // D = 1: slot of row r-2 = slot this row overwrites
+                        uint2 qv;
+                        if (FILTER) {
+                            const uint32_t kR = 0xB600B600u;              // -0.375
+                            const uint32_t hn[4] = {h0, h1, h2, h3};
+                            uint32_t zpost = zP[zs], zpre = 0;
+                            qv.x = __byte_perm(zA[zs][0], zA[zs][1], 0x6420);
+                            qv.y = __byte_perm(zA[zs][2], zA[zs][3], 0x6420);
+#pragma unroll
+                            for (int i = 0; i < VB / 2; i++) {
+                                zpost |= hfma2_u(hn[i], kR, zA[zs][i]);
+                                zpre |= hfma2_u(zA[zs][i], kR, hn[i]);
+                                zA[zs][i] = hn[i];
+                            }
+                            fl.zr[zi] = zpost;
+                            zP[zs] = zpre;
+                        } else {
+                            qv = wP[zs];
+                            wP[zs] = w;
+                        }
+                        zi++;
+                        store_row(N * ((G::S0 + u + A - 2) / D), qv);
                     }
-                    // ---- rows that received their last tap ----
+                    // ---- interpolated rows that received their last tap ----
                     {
                         int q = 0;
 #pragma unroll
                         for (int yr = ylo6<N, D>(s0); yr < yhi6<N, D>(s0); yr++) {
                             const int ph = (yr * D) % N;
-                            const int yoff = N * tq + yr;                 // output row relative to yit
+                            if (ph == 0) continue;
                             uint2 qv;
-                            bool doubt = false;
-                            if (ph == 0) {
-                                // centre row relative to this iteration's first row: u - A
-                                const uint8_t *crow = vit + (u - A) * SWM + ((u - A < 0) ? wrapseq[u] : 0);
-                                qv = *reinterpret_cast<const uint2 *>(crow);
-                            } else {
-                                qv.x = quantise4(res[q][0], res[q][1], res[q][2], res[q][3]);
-                                qv.y = quantise4(res[q][4], res[q][5], res[q][6], res[q][7]);
-                                if (MODE == 0) {
-                                    const float2 gg = make_float2(g2v, g2v);
-                                    const float2 b01 = __fadd2_rn(make_float2(res[q][0], res[q][1]), gg), b23 = __fadd2_rn(make_float2(res[q][2], res[q][3]), gg);
-                                    const float2 b45 = __fadd2_rn(make_float2(res[q][4], res[q][5]), gg), b67 = __fadd2_rn(make_float2(res[q][6], res[q][7]), gg);
-                                    const uint32_t bx = quantise4(b01.x, b01.y, b23.x, b23.y);
-                                    const uint32_t by = quantise4(b45.x, b45.y, b67.x, b67.y);
-                                    doubt = (qv.x != bx) || (qv.y != by);
-                                }
-                                q++;
+                            qv.x = quantise4(res[q][0], res[q][1], res[q][2], res[q][3]);
+                            qv.y = quantise4(res[q][4], res[q][5], res[q][6], res[q][7]);
+#ifndef LZB_ABL_NOVGUARD
+                            if (MODE == 0) {
+                                const float2 gg = make_float2(g2v, g2v);
+                                const float2 b01 = __fadd2_rn(make_float2(res[q][0], res[q][1]), gg), b23 = __fadd2_rn(make_float2(res[q][2], res[q][3]), gg);
+                                const float2 b45 = __fadd2_rn(make_float2(res[q][4], res[q][5]), gg), b67 = __fadd2_rn(make_float2(res[q][6], res[q][7]), gg);
+                                fl.dx[qi] = qv.x ^ quantise4(b01.x, b01.y, b23.x, b23.y);
+                                fl.dy[qi] = qv.y ^ quantise4(b45.x, b45.y, b67.x, b67.y);
                             }
-                            uint8_t *orow = op;
-                            op += opitch;
-                            if (CHECK && (yit + yoff < ys || yit + yoff >= ye)) continue;
-                            if (MODE == 0 && doubt) fl |= 1u << yoff;
-                            if (ST64) {
-                                *reinterpret_cast<uint2 *>(orow) = qv;
-                            } else {
-                                *reinterpret_cast<uint32_t *>(orow) = qv.x;
-                                if (v_second) *reinterpret_cast<uint32_t *>(orow + 4) = qv.y;
-                            }
+#else
+                            if (MODE == 0) { fl.dx[qi] = 0; fl.dy[qi] = 0; }
+#endif
+                            q++;
+                            qi++;
+                            store_row(N * tq + yr, qv);
                         }
                     }
                 }
-                if (MODE == 0) fixrows |= (unsigned long long)fl << (it * (N * VU / D));
+                if (MODE == 0) {
+                    // rare: some row of this iteration needs a second look (every row has been stored already)
+                    uint32_t any = 0;
+#pragma unroll
+                    for (int j = 0; j < NI_IT; j++) any |= fl.dx[j] | fl.dy[j];
+                    if (FILTER) {
+                        uint32_t anyz = 0;
+#pragma unroll
+                        for (int j = 0; j < NZ_IT; j++) anyz |= fl.zr[j];
+                        any |= anyz & zmask;
+                    }
+                    if (any != 0u)
+                        n_strict += v_fix_iter<A, N, D, FILTER ? KM : 0, VU, G::S0, G::RING, SWM, ST64>(
+                            p, vcol_s, (int)((uint32_t)(vit - vcol) / (uint32_t)SWM), yit, op, opitch, fl, zmask, valid_bytes - VB * tid, ys, ye);
+                }
                 vit += VU * SWM;
                 yit += N * VU / D;
-                // rows lr-A of the next iteration: one more iteration's worth of them lies inside this chunk
-#pragma unroll
-                for (int u = 0; u < VU; u++) wrapseq[u] = (u + VU * (it + 1) - A >= 0) ? 0 : wrapseq[u];
+                op += (long long)(N * VU / D) * opitch;
             }
         };
         if (interior) body(std::false_type{}); else body(std::true_type{});
-        if (MODE == 0) {
-            // rows [ylo(S0), ylo(S0) + YROWS) relative to ybase were stored in this chunk; later bits wait
-            constexpr uint32_t kDone = (uint32_t)((1ull << (ylo6<N, D>(G::S0) + G::YROWS)) - 1ull);
-            uint32_t todo = (uint32_t)fixrows & kDone;
-            fixrows = (fixrows & ~(unsigned long long)kDone) >> G::YROWS;
-            if (!p.strict_v_identity) {      // LANCZOS_FLAG_FAST_ALIGNED: phase-0 rows stay plain copies
-                uint32_t ph0rows = 0;
-#pragma unroll
-                for (int yy = 0; yy < 32; yy++)
-                    if ((yy * D) % N == 0) ph0rows |= 1u << yy;
-                todo &= ~ph0rows;
-            }
-            if (todo) {
-                // rows outside [ys, ye) were never stored (their bits can only come from the phase-0 test)
-                uint32_t inrange = 0;
-                if (!interior) {
-#pragma unroll 1
-                    for (int yy = 0; yy < 32; yy++)
-                        if (ybase + yy >= ys && ybase + yy < ye) inrange |= 1u << yy;
-                    todo &= inrange;
-                }
-                if (todo) {
-                    VFixArgs a;
-                    a.col = vcol; a.ocol = ocol; a.opitch = opitch; a.ybase = ybase; a.rs = rs;
-                    a.nbytes = min(VB, valid_bytes - VB * tid);
-                    a.rows = todo;
-                    n_strict += v_fix<A, N, D, KM, G::RING, SWM, VB>(p, a);
-                }
-            }
-        }
         ybase += G::YROWS;
         ocol += (long long)G::YROWS * opitch;
     };
 
     // ------------------------------ pipeline ------------------------------
     for (int chunk = 0; chunk < nchunks; chunk++) {
+#ifndef LZB_ABL_NOH
         h_pass(chunk);
+#else
+        mbar_wait(full0 + 8 * (chunk % G::STAGES), (chunk / G::STAGES) & 1);
+#endif
         __syncwarp();
         // every lane has read the TMA stage of this chunk: refill it with chunk + STAGES
         if (tid == 0 && chunk + G::STAGES < nchunks) issue(chunk + G::STAGES);
+#ifndef LZB_ABL_NOV
         if (v_active) v_pass(chunk);
+#endif
         // in-place top rows of the reference: replayed exactly once rows 0..alias_top_row+A are in the ring
         if (p.alias_rows > 0 && ys == 0 && v_active && chunk == (nchunks > 1 ? 1 : 0)) {
             AliasArgs a;
-            a.col = vcol; a.ocol = out_frame + obyte0 + VB * tid; a.opitch = opitch; a.rs = rs;
+            a.col = vcol; a.ocol = out_frame + vbyte0 + VB * tid; a.opitch = opitch; a.rs = rs;
             a.nbytes = min(VB, valid_bytes - VB * tid);
             alias_fix<A, N, D, G::RB, SWM, VB>(p, a);
         }
@@ -882,9 +1018,8 @@ int launch_v6_one(const KParams &k, const FastHostTables &t, int *alias_in_kerne
     EncodeFn encode = get_encode();
     if (!encode) return -1;
     const int row_bytes = k.out_w * C;
-    // one strip per warp: MAX_GROUPS H items wide (fewer if the image is narrower than that)
-    const int best_groups = std::min(G::MAX_GROUPS, (row_bytes + G::OUT_B - 1) / G::OUT_B);
-    const int sw = best_groups * G::OUT_B;
+    // one strip of SWV = 256 output bytes per warp
+    const int sw = G::SWV;
     const int strips = (row_bytes + sw - 1) / sw;
     const int vperiod0 = k.out_row0 / N;
     const int vperiods = (k.out_row0 + k.out_rows + N - 1) / N - vperiod0;
@@ -952,7 +1087,7 @@ int launch_v6_one(const KParams &k, const FastHostTables &t, int *alias_in_kerne
     p.out_frame_stride = k.out_frame_stride;
     p.in_w = k.in_w; p.in_h = k.in_h; p.out_w = k.out_w; p.out_h = k.out_h;
     p.out_row0 = k.out_row0; p.out_rows = k.out_rows; p.in_row0 = k.in_row0; p.in_rows = k.in_rows;
-    p.sw = sw; p.groups = best_groups; p.seg_periods = seg_periods; p.vperiod0 = vperiod0;
+    p.sw = sw; p.groups = G::MAX_GROUPS; p.seg_periods = seg_periods; p.vperiod0 = vperiod0;
     p.wdx = k.wdx; p.wdy = k.wdy;
     p.guard_h = k.guard_outer; p.guard_v = k.guard_asc;
     p.uniform_x = t.uniform_x; p.uniform_y = t.uniform_y;
@@ -1009,8 +1144,11 @@ int launch_v6(const KParams &k, const FastHostTables &t, int *kernel_id, int *al
         return st64 ? launch_v6_one<c, a, n, d, ph, kmask, LZB_W, 1, true>(k, t, alias_in_kernel, s)                        \
                     : launch_v6_one<c, a, n, d, ph, kmask, LZB_W, 1, false>(k, t, alias_in_kernel, s);                      \
     }
+    // the phase-0 rows are decided with taps 0..4 only (v_fix_phase0): needs the residue pattern plan.cpp checks
+    if (km != 0 && t.p0_half2[0] == 0xFC00FC00u) return -1;
     // a = 3: sin(2*pi) < 0 in double, so the |d| = 2 taps (k = 0 and k = 4) carry negative residues
     LZ6_CASE(3, 3, 2, 1, 8, 0x11, 1)
+#ifndef LZB_V6_DEV   // development builds (tools/build_variant.sh -DLZB_V6_DEV): the headline instance only
     LZ6_CASE(4, 3, 2, 1, 6, 0x11, 2)
     LZ6_CASE(4, 3, 3, 2, 4, 0x11, 3)
     LZ6_CASE(3, 2, 2, 1, 8, 0x0, 4)
@@ -1018,6 +1156,7 @@ int launch_v6(const KParams &k, const FastHostTables &t, int *kernel_id, int *al
     LZ6_CASE(1, 3, 2, 1, 24, 0x11, 8)
     LZ6_CASE(1, 3, 3, 2, 16, 0x11, 9)
     LZ6_CASE(1, 2, 2, 1, 24, 0x0, 10)
+#endif
 #undef LZ6_CASE
     return -1;
 }
