@@ -3,18 +3,24 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Workload (BASELINE.json configs[1]): 1920x1080 -> 3840x2160 RGB8, 2x, Lanczos-3.  One "step" is
-one pass of the hot path over a batch of `--frames` distinct synthetic frames per GPU (the batch is
-~2 GB per GPU, far larger than the 126 MB L2, so every step streams from HBM).  Weak scaling: each
-GPU gets its own batch; no data-path collective; NCCL is used only for the barrier and the
-max-over-ranks of the step time.
+Workload (BASELINE.json configs[1]): 1920x1080 -> 3840x2160 RGB8, 2x, Lanczos-3.  One "step" is one pass of
+the hot path over a batch of `--frames` distinct synthetic frames per GPU, ONE kernel launch (the batch is ~2 GB
+per GPU, far larger than the 126 MB L2, so every step streams from HBM).  Weak scaling: each GPU gets its own
+batch; no data-path collective; NCCL is used only for the barrier and the max-over-ranks of the step time.
+
+The kernel's speed depends on pixel values (the exact path re-evaluates samples the reference may truncate
+differently), so the batch is a 50/50 MIX: even frames image-like (SURVEY.md 8d ii: smooth + noise), odd frames
+uniform noise (8d i, the input BASELINE.md section 3 names and the worst case).  `value`, `roofline`, `e2e` and
+`cpu_baseline` are all measured on that mix with the default flags; `by_content` gives the two halves alone.
 
 Prints ONE JSON line (see the contract in the task statement):
   value        whole-job output Mpix/s, inputs resident in HBM, device-timed (CUDA events)
-  roofline     HBM roofline of the dominant kernel from a live CUDA-event timing
+  roofline     HBM roofline of the dominant kernel (the step IS one launch of it), same flags and content as value
   e2e          same metric through the host-buffer C-ABI call (pinned host memory, H2D+D2H inside)
   cpu_baseline the reference's own software path (oracle/_ref) on this box's host cores
-`--impl reference` times that CPU path alone (rank 0; other ranks exit).
+  c3, c4, c5_bands  the other BASELINE configs at their literal batch sizes (256 frames sharded over the GPUs,
+               1024/8 = 128 frames per GPU, one 16384^2 image in row bands)
+`--impl reference` times the CPU path alone (rank 0; other ranks exit).
 """
 import argparse
 import json
@@ -30,13 +36,10 @@ sys.path.insert(0, ROOT)
 # name -> (in_w, in_h, out_w, out_h, channels, a, N, D, default frames per GPU per step, label)
 WORKLOADS = {
     "c2": (1920, 1080, 3840, 2160, 3, 3, 2, 1, 64, "1920x1080->3840x2160 RGB8 2x Lanczos-3 (BASELINE configs[1])"),
-    "c3": (2560, 1440, 3840, 2160, 4, 3, 3, 2, 32, "2560x1440->3840x2160 RGBA8 3/2 Lanczos-3 (BASELINE configs[2], frames sharded over GPUs)"),
-    "c4": (3840, 2160, 7680, 4320, 3, 3, 2, 1, 16, "3840x2160->7680x4320 RGB8 2x Lanczos-3 (BASELINE configs[3], frames sharded over GPUs)"),
+    "c3": (2560, 1440, 3840, 2160, 4, 3, 3, 2, 256, "2560x1440->3840x2160 RGBA8 3/2 Lanczos-3, batch of 256 frames sharded over the GPUs (BASELINE configs[2])"),
+    "c4": (3840, 2160, 7680, 4320, 3, 3, 2, 1, 128, "3840x2160->7680x4320 RGB8 2x Lanczos-3, 1024 frames over 8 GPUs = 128 frames per GPU (BASELINE configs[3])"),
 }
-IN_W, IN_H, OUT_W, OUT_H, CH, A, SN, SD, DEF_FRAMES, WORKLOAD = WORKLOADS["c2"]
-ALGO_BYTES_PER_FRAME = IN_W * IN_H * CH + OUT_W * OUT_H * CH      # 31,104,000 for c2
-OUT_PX_PER_FRAME = OUT_W * OUT_H
-# CPU sample of the same workload: a 1920x135 band -> 3840x270 (1/8 frame), reference compiled for it
+# CPU sample of the headline workload: a 1920x135 band -> 3840x270 (1/8 frame), reference compiled for it
 CPU_SAMPLE_CFG = (1920, 135, 3840, 270, 2, 1, 3, 3)
 
 
@@ -48,14 +51,15 @@ def measured_hbm_peak():
         return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
 
 
-def ncu_traffic_per_launch(frames):
-    """DRAM bytes per launch from the committed ncu capture, scaled per frame (None if absent)."""
+def ncu_traffic_per_frame():
+    """DRAM bytes per frame of the headline kernel from the committed `ncu --set full` capture (None if absent).
+    A constant from profiles/traffic.json: ncu cannot run inside the timed benchmark."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
             t = json.load(fh)
-        return float(t["dram_bytes_per_frame"]) * frames
+        return float(t["dram_bytes_per_frame"]), t.get("source", "profiles/traffic.json")
     except Exception:
-        return None
+        return None, None
 
 
 class ClockSampler:
@@ -111,8 +115,12 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ------------------------------------------------------------------------------------------------------
+# the reference's own CPU path (the one place outside tests/ that executes oracle/)
+# ------------------------------------------------------------------------------------------------------
 def run_reference_cpu(steps, warmup, threads=None):
-    """The reference's own software path (full_TB.h:29-96 compiled into oracle/_ref) on host cores."""
+    """The reference's own software path (full_TB.h:29-96 compiled into oracle/_ref) on host cores, on the same
+    50/50 content mix as the GPU arm: even threads image-like bands, odd threads uniform noise."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
     import oracle_py as O
@@ -123,7 +131,16 @@ def run_reference_cpu(steps, warmup, threads=None):
     have_ref = os.path.exists(O.ref_path(cfg))
     if not have_ref:
         kind = "port"
-    imgs = [O.xorshift_bytes(c * ih * iw, O.SEED + t).reshape(c, ih, iw) for t in range(cores)]
+
+    def band(t):
+        noise = O.xorshift_bytes(c * ih * iw, O.SEED + t).reshape(c, ih, iw)
+        if t % 2 == 1:
+            return noise
+        yy, xx = np.mgrid[0:ih, 0:iw]
+        img = np.stack([128 + 90 * np.sin(0.05 * xx + ch + 0.3 * t) * np.cos(0.037 * yy) for ch in range(c)])
+        return np.ascontiguousarray(np.clip(img + ((noise.astype(np.int32) & 15) - 8), 0, 255).astype(np.uint8))
+
+    imgs = [band(t) for t in range(cores)]
 
     def one(t):
         if have_ref:
@@ -147,122 +164,235 @@ def run_reference_cpu(steps, warmup, threads=None):
         step()
     dt = time.perf_counter() - t0
     px = steps * cores * ow * oh
-    sample = (f"{cores} threads x {steps} steps, each thread one 1920x135->3840x270 RGB8 band (1/8 of a frame) of "
-              f"uniform noise through {'oracle/_ref (reference full_TB.h:29-96 compiled as is)' if have_ref else 'the oracle literal port'}")
+    sample = (f"{cores} threads x {steps} steps, each thread one 1920x135->3840x270 RGB8 band (1/8 of a frame; even threads "
+              f"image-like, odd threads uniform noise: the GPU arm's 50/50 mix) through "
+              f"{'oracle/_ref (reference full_TB.h:29-96 compiled as is)' if have_ref else 'the oracle literal port'}")
     return {"value": px / dt / 1e6, "unit": "Mpix/s", "cores": cores, "kind": kind, "sample": sample,
             "seconds": dt, "ms_per_step": dt / steps * 1e3}
 
 
-def run_bands(args, rank, local_rank, world):
-    """BASELINE configs[4]: one 16384x16384 RGB8 image upscaled x1.7 (17/10, out = floor(in*17/10)),
-    output rows split into one band per GPU, each GPU holding only its own input rows + halo.
-    Strong scaling: the image is fixed, value = its output pixels / max-over-ranks step time."""
-    import numpy as np
-    import torch
-    import lanczos_hls_b200 as lz
-    from lanczos_hls_b200.sharding import band_range
+# ------------------------------------------------------------------------------------------------------
+# GPU helpers
+# ------------------------------------------------------------------------------------------------------
+class Ctx:
+    """torch / NCCL plumbing of one rank."""
 
-    S = args.band_size
-    iw = ih = S
-    ow = oh = S * 17 // 10
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+    def __init__(self, rank, local_rank, world):
+        import torch
+        self.torch = torch
+        self.rank, self.local_rank, self.world = rank, local_rank, world
+        torch.cuda.set_device(local_rank)
+        self.dev = torch.device("cuda", local_rank)
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+        self.gen = torch.Generator(device=self.dev)
+        self.gen.manual_seed(0x9E3779B9 + rank)
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.item()
+
+    def timed(self, fn, steps, warm=3):
+        """K calls of fn bracketed by barrier + synchronize, CUDA events on the launching stream, max over ranks.
+        Returns ms per call."""
+        torch = self.torch
+        for _ in range(warm):
+            fn()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1)) / steps
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def fill_frames(ctx, d_in, content, frame0=0):
+    """Synthetic frames in place: image-like = 128 + 90 sin(0.05x + c + 0.3f) cos(0.037y) + U[-8,7] (SURVEY.md 8d ii),
+    noise = uniform bytes (8d i), mix = even frames image-like, odd frames noise."""
+    torch = ctx.torch
+    F, H, W, C = d_in.shape
+    yy = torch.arange(H, device=ctx.dev, dtype=torch.float32).view(H, 1, 1)
+    xx = torch.arange(W, device=ctx.dev, dtype=torch.float32).view(1, W, 1)
+    cc = torch.arange(C, device=ctx.dev, dtype=torch.float32).view(1, 1, C)
+    for f in range(F):
+        if content == "noise" or (content == "mix" and f % 2 == 1):
+            d_in[f] = torch.randint(0, 256, (H, W, C), dtype=torch.uint8, device=ctx.dev, generator=ctx.gen)
+        else:
+            base = 128 + 90 * torch.sin(0.05 * xx + cc + 0.3 * (frame0 + f)) * torch.cos(0.037 * yy)
+            base += torch.randint(-8, 8, (H, W, C), device=ctx.dev, generator=ctx.gen)
+            d_in[f] = base.clamp_(0, 255).to(torch.uint8)
+    torch.cuda.synchronize()
+
+
+def bench_batch(ctx, lz, name, frames, steps, flags=0, contents=("mix",)):
+    """One BASELINE batch config on this rank's GPU: `frames` frames per GPU, one launch per step.
+    Returns {content: ms per step} (max over ranks) plus the kernel id."""
+    torch = ctx.torch
+    iw, ih, ow, oh, ch, a, sn, sd, _, _ = WORKLOADS[name]
+    d_in = torch.empty((frames, ih, iw, ch), dtype=torch.uint8, device=ctx.dev)
+    d_out = torch.empty((frames, oh, ow, ch), dtype=torch.uint8, device=ctx.dev)
+
+    def step():
+        lz.upscale_batch_device(d_in, d_out, a=a, scale_n=sn, scale_d=sd, flags=flags)
+
+    res = {}
+    for content in contents:
+        fill_frames(ctx, d_in, content)
+        step()
         torch.cuda.synchronize()
+        res[content] = ctx.timed(step, steps)
+    st = lz.stats()
+    del d_in, d_out
+    torch.cuda.empty_cache()
+    return res, st["kernel_id"], st["kernel_launches"]
 
+
+def summarise_batch(name, frames, n_gpus, ms, peak):
+    iw, ih, ow, oh, ch = WORKLOADS[name][:5]
+    algo = frames * (iw * ih * ch + ow * oh * ch)
+    out = {}
+    for content, t in ms.items():
+        out[content] = {"value": n_gpus * frames * ow * oh / (t * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": t,
+                        "roofline_frac": algo / (t * 1e-3) / 1e9 / peak}
+    return out
+
+
+def bench_bands(ctx, lz, size, steps, contents=("image_like",)):
+    """BASELINE configs[4]: one size x size RGB8 image upscaled x1.7 (17/10, out = floor(in*17/10)), output rows
+    split into one band per GPU, each GPU holding only its own input rows + halo.  Strong scaling: the image is
+    fixed, value = its output pixels / max-over-ranks step time."""
+    torch = ctx.torch
+    from lanczos_hls_b200.sharding import band_range
+    iw = ih = size
+    ow = oh = size * 17 // 10
     desc = lz.make_desc(iw, ih, ow, oh, 3, 3, 17, 10)
-    r0, r1 = band_range(oh, rank, world)
+    r0, r1 = band_range(oh, ctx.rank, ctx.world)
     in0, inn = lz.band_input_rows(desc, r0, r1 - r0)
-    g = torch.Generator(device=dev)
-    g.manual_seed(1234 + rank)
-    yy = torch.arange(in0, in0 + inn, device=dev, dtype=torch.float32).view(inn, 1, 1)
-    xx = torch.arange(iw, device=dev, dtype=torch.float32).view(1, iw, 1)
-    cc = torch.arange(3, device=dev, dtype=torch.float32).view(1, 1, 3)
-    d_in = (128 + 90 * torch.sin(0.05 * xx + cc) * torch.cos(0.037 * yy)
-            + torch.randint(-8, 8, (inn, iw, 3), device=dev, generator=g)).clamp_(0, 255).to(torch.uint8)
-    d_out = torch.empty((r1 - r0, ow, 3), dtype=torch.uint8, device=dev)
+    d_in = torch.empty((inn, iw, 3), dtype=torch.uint8, device=ctx.dev)
+    d_out = torch.empty((r1 - r0, ow, 3), dtype=torch.uint8, device=ctx.dev)
 
     def step():
         lz.upscale_band_device(desc, d_in, d_out, r0, r1 - r0, in0, inn)
 
-    step()
-    torch.cuda.synchronize()
-    st = lz.stats()
-    for _ in range(max(args.warmup, 3)):
+    res = {}
+    for content in contents:
+        if content == "noise":
+            d_in.copy_(torch.randint(0, 256, (inn, iw, 3), dtype=torch.uint8, device=ctx.dev, generator=ctx.gen))
+        else:
+            yy = torch.arange(in0, in0 + inn, device=ctx.dev, dtype=torch.float32).view(inn, 1, 1)
+            xx = torch.arange(iw, device=ctx.dev, dtype=torch.float32).view(1, iw, 1)
+            cc = torch.arange(3, device=ctx.dev, dtype=torch.float32).view(1, 1, 3)
+            for a0 in range(0, inn, 1024):       # in slabs: the float temporaries of a 16384-wide band are large
+                a1 = min(inn, a0 + 1024)
+                d_in[a0:a1] = (128 + 90 * torch.sin(0.05 * xx + cc) * torch.cos(0.037 * yy[a0:a1])
+                               + torch.randint(-8, 8, (a1 - a0, iw, 3), device=ctx.dev, generator=ctx.gen)).clamp_(0, 255).to(torch.uint8)
         step()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+        torch.cuda.synchronize()
+        res[content] = ctx.timed(step, steps)
+    st = lz.stats()
+    geo = {"iw": iw, "ih": ih, "ow": ow, "oh": oh, "in0": in0, "inn": inn, "r0": r0, "r1": r1}
+    return res, st, geo, (d_in, d_out, step)
+
+
+def bands_line(args, ctx, lz):
+    """--workload c5: the row-band config as its own JSON line (strong scaling)."""
+    torch = ctx.torch
+    steps = args.steps
+    sampler = ClockSampler(ctx.local_rank)
+    if ctx.rank == 0:
         sampler.start()
         time.sleep(0.3)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
+    res, st, geo, (d_in, d_out, step) = bench_bands(ctx, lz, args.band_size, steps, contents=("image_like", "noise"))
     # a band step takes a few ms: keep the same kernel running (untimed) until the 50 ms clock sampler has seen it
     t_load = time.perf_counter()
     while time.perf_counter() - t_load < 0.5:
         step()
         torch.cuda.synchronize()
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step = t.item() / args.steps
-
+    clocks = sampler.stop() if ctx.rank == 0 else None
+    iw, ih, ow, oh, inn = geo["iw"], geo["ih"], geo["ow"], geo["oh"], geo["inn"]
+    rows = geo["r1"] - geo["r0"]
     # end to end: the band's input rows from pinned host memory, the band's output rows back to it
-    lz.bind_host_to_device(local_rank)                   # pinned buffers land next to this rank's GPU
+    lz.bind_host_to_device(ctx.local_rank)
     hin = lz.PinnedBuffer(inn * iw * 3)
-    hout = lz.PinnedBuffer((r1 - r0) * ow * 3)
+    hout = lz.PinnedBuffer(rows * ow * 3)
     hin.array[:] = d_in.reshape(-1).cpu().numpy()
     h_in_t = torch.from_numpy(hin.array).view(inn, iw, 3)
-    h_out_t = torch.from_numpy(hout.array).view(r1 - r0, ow, 3)
-    e_steps = max(2, min(args.steps, 4))
-    barrier()
+    h_out_t = torch.from_numpy(hout.array).view(rows, ow, 3)
+    e_steps = max(2, min(steps, 4))
+    ctx.barrier()
     t0 = time.perf_counter()
     for _ in range(e_steps):
         d_in.copy_(h_in_t, non_blocking=True)
         step()
         h_out_t.copy_(d_out, non_blocking=True)
     torch.cuda.synchronize()
-    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+    te = ctx.max_over_ranks(time.perf_counter() - t0)
+    if ctx.rank != 0:
         return
     peak, peak_src = measured_hbm_peak()
     algo = iw * ih * 3 + ow * oh * 3
-    achieved = algo / world / (ms_per_step * 1e-3) / 1e9      # per GPU (bands are equal to within one row)
+    ms = res["image_like"]
+    achieved = algo / ctx.world / (ms * 1e-3) / 1e9      # per GPU (bands are equal to within one row)
     line = {
-        "metric": "output Mpix/s", "value": ow * oh / (ms_per_step * 1e-3) / 1e6, "unit": "Mpix/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "metric": "output Mpix/s", "value": ow * oh / (ms * 1e-3) / 1e6, "unit": "Mpix/s", "n_gpus": ctx.world,
+        "steps": steps, "warmup": 3, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32 (f64 exact re-evaluation near integers)", "data": "synthetic",
         "config": {"workload": f"single {iw}x{ih} -> {ow}x{oh} RGB8 x1.7 (17/10) image, one row band per GPU with halo rows "
-                               "(BASELINE configs[4])", "content": "smooth", "kernel_id": st["kernel_id"],
-                   "l2": f"inputs larger than L2: {algo / world / 1e6:.0f} MB streamed per GPU per step"},
+                               "(BASELINE configs[4])", "content": "image_like", "kernel_id": st["kernel_id"],
+                   "l2": f"inputs larger than L2: {algo / ctx.world / 1e6:.0f} MB streamed per GPU per step"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "peak_source": peak_src, "kernel": "main kernel of the band (whole step: includes the top-rows kernel in band 0)",
-                     "algorithmic_bytes_per_launch": algo / world},
+                     "algorithmic_bytes_per_launch": algo / ctx.world},
+        "by_content": {k: {"value": ow * oh / (v * 1e-3) / 1e6, "ms_per_step": v} for k, v in res.items()},
         "cpu_baseline": None,
-        "e2e": {"value": ow * oh * e_steps / te.item() / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": inn * iw * 3,
-                "d2h_bytes_per_step": (r1 - r0) * ow * 3, "steps": e_steps,
+        "e2e": {"value": ow * oh * e_steps / te / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": inn * iw * 3,
+                "d2h_bytes_per_step": rows * ow * 3, "steps": e_steps,
                 "api": "pinned host band -> lanczos_b200_upscale_band -> pinned host band"},
-        "gpu_launches": st["kernel_launches"] * args.steps, "clocks": clocks,
+        "gpu_launches": st["kernel_launches"] * steps, "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+
+
+def pcie_ceiling(ctx, hin, hout, d_in, d_out):
+    """Plain pinned copies of the e2e buffers, both directions at once on two streams: the platform's ceiling for
+    any host-buffer path on this rank while the other ranks do the same (max over ranks of the time)."""
+    torch = ctx.torch
+    s_up, s_dn = torch.cuda.Stream(device=ctx.dev), torch.cuda.Stream(device=ctx.dev)
+    h_in_t, h_out_t = torch.from_numpy(hin.array), torch.from_numpy(hout.array)
+    di, do = d_in.reshape(-1)[: hin.nbytes], d_out.reshape(-1)[: hout.nbytes]
+
+    def both():
+        with torch.cuda.stream(s_up):
+            di.copy_(h_in_t, non_blocking=True)
+        with torch.cuda.stream(s_dn):
+            h_out_t.copy_(do, non_blocking=True)
+
+    both()
+    ctx.barrier()
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        both()
+    torch.cuda.synchronize()
+    dt = ctx.max_over_ranks(time.perf_counter() - t0) / reps
+    return {"h2d_gbs": hin.nbytes / dt / 1e9, "d2h_gbs": hout.nbytes / dt / 1e9, "seconds_per_step_at_ceiling": dt,
+            "how": "plain pinned cudaMemcpyAsync of the same buffers, H2D and D2H concurrently on two streams, slowest rank"}
 
 
 def main():
@@ -275,40 +405,24 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c5"],
                     help="c2 = headline (BASELINE configs[1]); c5 = one large image in row bands (BASELINE configs[4])")
     ap.add_argument("--band-size", type=int, default=16384, help="c5: input side length")
-    ap.add_argument("--content", default="smooth", choices=["noise", "smooth"],
-                    help="smooth = SURVEY 8d(ii) image-like content (default); noise = 8d(i) uniform noise, the worst "
-                         "case for the exact re-evaluation path (reported as worst_case in the JSON line)")
+    ap.add_argument("--content", default="mix", choices=["mix", "noise", "image_like"],
+                    help="mix (default) = even frames image-like (SURVEY 8d ii), odd frames uniform noise (8d i)")
     ap.add_argument("--e2e-frames", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the c3 / c4 / c5_bands / single-frame sub-benchmarks")
     ap.add_argument("--flags", type=int, default=0)
     args = ap.parse_args()
-    global IN_W, IN_H, OUT_W, OUT_H, CH, A, SN, SD, DEF_FRAMES, WORKLOAD, ALGO_BYTES_PER_FRAME, OUT_PX_PER_FRAME
-    if args.workload == "c5" and args.impl == "ours":
-        _rank, _lrank, _world = (int(os.environ.get(k, "0")) for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"))
-        if max(_world, 1) == 1 and args.gpus > 1:
-            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
-                   "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
-            os.execv(sys.executable, cmd)
-        return run_bands(args, _rank, _lrank, max(_world, 1))
-    if args.workload == "c5":
-        args.workload = "c2"          # the reference arm always samples the headline workload
-    IN_W, IN_H, OUT_W, OUT_H, CH, A, SN, SD, DEF_FRAMES, WORKLOAD = WORKLOADS[args.workload]
-    ALGO_BYTES_PER_FRAME = IN_W * IN_H * CH + OUT_W * OUT_H * CH
-    OUT_PX_PER_FRAME = OUT_W * OUT_H
-    if args.frames <= 0:
-        args.frames = DEF_FRAMES
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world == 1 and args.gpus > 1:
+    if world == 1 and args.gpus > 1 and args.impl == "ours":
         # launched directly: re-exec under torchrun, one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
         os.execv(sys.executable, cmd)
     n_gpus = world
-    warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     if args.impl == "reference":
         if rank != 0:
@@ -320,7 +434,7 @@ def main():
             "impl": "reference", "metric": "output Mpix/s", "value": res["value"], "unit": "Mpix/s",
             "n_gpus": n_gpus, "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": res["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": res["sample"]},
+            "config": {"workload": WORKLOADS["c2"][9], "content": "mix", "sample": res["sample"]},
             "cpu_baseline": {"value": res["value"], "unit": "Mpix/s", "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]},
             "e2e": {"value": res["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -334,38 +448,41 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+    ctx = Ctx(rank, local_rank, world)
     lz.lib()
+    if args.workload == "c5":
+        bands_line(args, ctx, lz)
+        ctx.close()
+        return
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
+    name = args.workload
+    IN_W, IN_H, OUT_W, OUT_H, CH, A, SN, SD, DEF_FRAMES, WORKLOAD = WORKLOADS[name]
+    if name == "c3" and args.frames <= 0:
+        args.frames = max(1, DEF_FRAMES // n_gpus)       # 256 frames sharded over the GPUs
+    F = args.frames if args.frames > 0 else DEF_FRAMES
+    algo_per_frame = IN_W * IN_H * CH + OUT_W * OUT_H * CH      # 31,104,000 for c2
+    px_per_frame = OUT_W * OUT_H
+    warmup = max(args.warmup, 3)
+    dev = ctx.dev
+    peak, peak_src = measured_hbm_peak()
 
-    F = args.frames
-    g = torch.Generator(device=dev)
-    g.manual_seed(0x9E3779B9 + rank)
-    if args.content == "noise":
-        d_in = torch.randint(0, 256, (F, IN_H, IN_W, CH), dtype=torch.uint8, device=dev, generator=g)
-    else:
-        yy = torch.arange(IN_H, device=dev, dtype=torch.float32).view(1, IN_H, 1, 1)
-        xx = torch.arange(IN_W, device=dev, dtype=torch.float32).view(1, 1, IN_W, 1)
-        cc = torch.arange(CH, device=dev, dtype=torch.float32).view(1, 1, 1, CH)
-        ff = torch.arange(F, device=dev, dtype=torch.float32).view(F, 1, 1, 1)
-        base = 128 + 90 * torch.sin(0.05 * xx + cc + 0.3 * ff) * torch.cos(0.037 * yy)
-        noise = torch.randint(-8, 8, (F, IN_H, IN_W, CH), device=dev, generator=g)
-        d_in = (base + noise).clamp_(0, 255).to(torch.uint8)
-        del base, noise
+    d_in = torch.empty((F, IN_H, IN_W, CH), dtype=torch.uint8, device=dev)
     d_out = torch.empty((F, OUT_H, OUT_W, CH), dtype=torch.uint8, device=dev)
 
     def step(flags=args.flags):
         lz.upscale_batch_device(d_in, d_out, a=A, scale_n=SN, scale_d=SD, flags=flags)
 
+    # the two halves alone, then the mix (which stays in d_in for everything that follows)
+    by_content = {}
+    others = [c for c in ("image_like", "noise") if c != args.content]
+    for content in others:
+        fill_frames(ctx, d_in, content)
+        step()
+        torch.cuda.synchronize()
+        t = ctx.timed(step, max(3, min(args.steps, 20)))
+        by_content[content] = {"value": n_gpus * F * px_per_frame / (t * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": t,
+                               "roofline_frac": F * algo_per_frame / (t * 1e-3) / 1e9 / peak}
+    fill_frames(ctx, d_in, args.content)
     step()
     step(args.flags | lz.FLAG_NO_ALIAS)   # builds the second plan (tables + upload) outside every timed region
     torch.cuda.synchronize()
@@ -378,72 +495,31 @@ def main():
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    barrier()
+    ctx.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    # dominant kernel alone (ping-pong flag: no top-rows kernel), CUDA events on the launching stream
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record()
-    for _ in range(args.steps):
-        step(args.flags | lz.FLAG_NO_ALIAS)
-    k1.record()
-    torch.cuda.synchronize()
-    kernel_ms = k0.elapsed_time(k1) / args.steps
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step = t.item() / args.steps
-    value = n_gpus * F * OUT_PX_PER_FRAME / (ms_per_step * 1e-3) / 1e6
-
-    # worst case for the exact path: uniform noise (every flat/phase-0 shortcut fails as often as it can)
-    worst = None
-    if args.content != "noise":
-        saved = d_in
-        d_in = torch.randint(0, 256, (F, IN_H, IN_W, CH), dtype=torch.uint8, device=dev, generator=g)
-        for _ in range(3):
-            step()
-        barrier()
-        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        w0.record()
-        for _ in range(args.steps):
-            step()
-        w1.record()
-        barrier()
-        tw = torch.tensor([w0.elapsed_time(w1)], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
-        worst = {"content": "uniform noise", "value": n_gpus * F * OUT_PX_PER_FRAME / (tw.item() / args.steps * 1e-3) / 1e6,
-                 "unit": "Mpix/s", "ms_per_step": tw.item() / args.steps}
-        d_in = saved
+    ctx.barrier()
+    ms_per_step = ctx.max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    ms_local = e0.elapsed_time(e1) / args.steps
+    value = n_gpus * F * px_per_frame / (ms_per_step * 1e-3) / 1e6
+    by_content[args.content] = {"value": value, "unit": "Mpix/s", "ms_per_step": ms_per_step,
+                                "roofline_frac": F * algo_per_frame / (ms_local * 1e-3) / 1e9 / peak}
 
     # ---- tolerance mode of the north star ("at most 1 LSB, exact-match fraction stated"): V pass in plain fp32 ----
     tol = None
     if not (args.flags & lz.FLAG_TOLERANCE_1LSB):
-        tflags = args.flags | lz.FLAG_TOLERANCE_1LSB | lz.FLAG_NO_ALIAS
-        ref_out = d_out.clone() if F * OUT_PX_PER_FRAME * CH <= (4 << 30) else None
+        tflags = args.flags | lz.FLAG_TOLERANCE_1LSB
+        ref_out = d_out.clone() if F * px_per_frame * CH <= (4 << 30) else None
         if ref_out is not None:
-            step(args.flags | lz.FLAG_NO_ALIAS)
+            step()
             ref_out.copy_(d_out)
-        for _ in range(3):
-            step(tflags)
-        barrier()
-        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        q0.record()
-        for _ in range(args.steps):
-            step(tflags)
-        q1.record()
-        barrier()
-        tt = torch.tensor([q0.elapsed_time(q1)], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        tol_ms = tt.item() / args.steps
-        tol = {"flag": "LANCZOS_FLAG_TOLERANCE_1LSB", "value": n_gpus * F * OUT_PX_PER_FRAME / (tol_ms * 1e-3) / 1e6,
-               "unit": "Mpix/s", "ms_per_step": tol_ms,
+        tol_ms = ctx.timed(lambda: step(tflags), args.steps)
+        tol = {"flag": "LANCZOS_FLAG_TOLERANCE_1LSB", "value": n_gpus * F * px_per_frame / (tol_ms * 1e-3) / 1e6,
+               "unit": "Mpix/s", "ms_per_step": tol_ms, "content": args.content,
+               "roofline_frac": F * algo_per_frame / (tol_ms * 1e-3) / 1e9 / peak,
                "note": "H pass bit-exact, V pass plain fp32: every byte within 1 LSB of the reference"}
         if ref_out is not None:
             neq = (d_out != ref_out)
@@ -454,7 +530,7 @@ def main():
     # ---- BASELINE configs[1] read literally: ONE frame per call (lanczos_b200_upscale), the frames of the batch in
     # turn so the working set stays larger than L2; on one stream and round-robin over four ----
     single = None
-    if args.workload in WORKLOADS:
+    if not args.no_extra:
         import ctypes as C
         L = lz.lib()
         desc = lz.make_desc(IN_W, IN_H, OUT_W, OUT_H, CH, A, SN, SD, flags=args.flags)
@@ -464,7 +540,7 @@ def main():
         streams = [torch.cuda.Stream(device=dev) for _ in range(4)]
         sp = [C.c_void_p(st.cuda_stream) for st in streams]
         dref = C.byref(desc)
-        single = {"call": "lanczos_b200_upscale, one frame per launch, frames of the batch in turn"}
+        single = {"call": "lanczos_b200_upscale, one frame per launch, frames of the batch in turn", "content": args.content}
         rounds = max(2, min(args.steps, 10))
         for ns in (1, 4):
             def run():
@@ -474,7 +550,7 @@ def main():
                         L.lanczos_b200_upscale(dref, pi, po, local_rank, sp[i % ns])
                         i += 1
             run()
-            barrier()
+            ctx.barrier()
             s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s0.record(streams[0])
             for st in streams[1:ns]:
@@ -483,12 +559,9 @@ def main():
             for st in streams[1:ns]:
                 streams[0].wait_stream(st)
             s1.record(streams[0])
-            barrier()
-            tsf = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
-            if dist is not None:
-                dist.all_reduce(tsf, op=dist.ReduceOp.MAX)
-            us = tsf.item() * 1e3 / (rounds * F)
-            single["streams_%d" % ns] = {"value": n_gpus * OUT_PX_PER_FRAME / (us * 1e-6) / 1e6, "unit": "Mpix/s", "us_per_frame": us}
+            ctx.barrier()
+            us = ctx.max_over_ranks(s0.elapsed_time(s1)) * 1e3 / (rounds * F)
+            single["streams_%d" % ns] = {"value": n_gpus * px_per_frame / (us * 1e-6) / 1e6, "unit": "Mpix/s", "us_per_frame": us}
 
     clocks = sampler.stop() if rank == 0 else None      # sampled over the timed device loops above
 
@@ -499,61 +572,84 @@ def main():
         numa_cpus = lz.bind_host_to_device(local_rank)      # pinned buffers below land next to this rank's GPU
         hin = lz.PinnedBuffer(Fe * IN_H * IN_W * CH)
         hout = lz.PinnedBuffer(Fe * OUT_H * OUT_W * CH)
-        hin.array[:] = d_in[:Fe].reshape(-1).cpu().numpy() if Fe <= F else np.resize(d_in.reshape(-1).cpu().numpy(), hin.nbytes)
+        hin.array[:] = d_in[:Fe].reshape(-1).cpu().numpy()
         h_in = hin.array.reshape(Fe, IN_H, IN_W, CH)
         h_out = hout.array.reshape(Fe, OUT_H, OUT_W, CH)
         e_steps = max(3, min(args.steps, 8))
         lz.upscale(h_in, OUT_W, OUT_H, a=A, scale_n=SN, scale_d=SD, flags=args.flags, device=local_rank, out=h_out)
-        barrier()
+        ctx.barrier()
         t0 = time.perf_counter()
         for _ in range(e_steps):
             lz.upscale(h_in, OUT_W, OUT_H, a=A, scale_n=SN, scale_d=SD, flags=args.flags, device=local_rank, out=h_out)
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if os.environ.get("LZB_BENCH_DEBUG"):
-            print(f"[rank {rank}] e2e dt {dt * 1e3 / e_steps:.2f} ms per step", file=sys.stderr, flush=True)
-        te = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": n_gpus * Fe * e_steps * OUT_PX_PER_FRAME / te.item() / 1e6, "unit": "Mpix/s",
+        dt = ctx.max_over_ranks(time.perf_counter() - t0)
+        ceiling = pcie_ceiling(ctx, hin, hout, d_in, d_out)
+        e2e = {"value": n_gpus * Fe * e_steps * px_per_frame / dt / 1e6, "unit": "Mpix/s",
                "h2d_bytes_per_step": Fe * IN_H * IN_W * CH, "d2h_bytes_per_step": Fe * OUT_H * OUT_W * CH,
-               "frames_per_step": Fe, "steps": e_steps, "ms_per_step": te.item() / e_steps * 1e3,
+               "frames_per_step": Fe, "steps": e_steps, "ms_per_step": dt / e_steps * 1e3, "content": args.content,
                "api": "lanczos_b200_upscale_host (pinned host buffers, 3 streams)",
-               "numa_bound_cpus": len(numa_cpus) if numa_cpus else 0}
+               "numa_bound_cpus": len(numa_cpus) if numa_cpus else 0,
+               "pcie_ceiling": ceiling, "pcie_ceiling_gbs": ceiling["h2d_gbs"] + ceiling["d2h_gbs"],
+               "frac_of_pcie_ceiling": ceiling["seconds_per_step_at_ceiling"] / (dt / e_steps)}
         hin.free()
         hout.free()
 
+    del d_in, d_out
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs at their literal batch sizes (device-timed, same 50/50 mix) ----
+    extra = {}
+    if not args.no_extra and name == "c2":
+        sub_steps = max(3, min(args.steps, 10))
+        for sub in ("c3", "c4"):
+            frames = max(1, WORKLOADS[sub][8] // n_gpus) if sub == "c3" else WORKLOADS[sub][8]
+            ms, kid, _ = bench_batch(ctx, lz, sub, frames, sub_steps, flags=args.flags, contents=("mix", "image_like"))
+            extra[sub] = {"workload": WORKLOADS[sub][9], "frames_per_gpu": frames, "kernel_id": kid,
+                          "scaling": "strong (256 frames in total)" if sub == "c3" else "weak (128 frames per GPU)",
+                          "by_content": summarise_batch(sub, frames, n_gpus, ms, peak)}
+            extra[sub].update(extra[sub]["by_content"]["mix"])
+        res, st, geo, keep = bench_bands(ctx, lz, args.band_size, max(3, min(args.steps, 5)), contents=("image_like", "noise"))
+        del keep
+        torch.cuda.empty_cache()
+        algo5 = geo["iw"] * geo["ih"] * 3 + geo["ow"] * geo["oh"] * 3
+        extra["c5_bands"] = {"workload": f"single {geo['iw']}x{geo['ih']} -> {geo['ow']}x{geo['oh']} RGB8 x1.7 (17/10), one row band per GPU "
+                                         "with its own halo rows (BASELINE configs[4])", "scaling": "strong", "kernel_id": st["kernel_id"],
+                             "by_content": {k: {"value": geo["ow"] * geo["oh"] / (v * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": v,
+                                                "roofline_frac_per_gpu": algo5 / n_gpus / (v * 1e-3) / 1e9 / peak} for k, v in res.items()}}
+        extra["c5_bands"].update(extra["c5_bands"]["by_content"]["image_like"])
+
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        ctx.close()
         return
 
-    peak, peak_src = measured_hbm_peak()
-    achieved = F * ALGO_BYTES_PER_FRAME / (kernel_ms * 1e-3) / 1e9
-    if tol is not None:
-        tol["roofline_frac"] = F * ALGO_BYTES_PER_FRAME / (tol["ms_per_step"] * 1e-3) / 1e9 / peak
+    achieved = F * algo_per_frame / (ms_local * 1e-3) / 1e9
+    traffic_pf, traffic_src = ncu_traffic_per_frame() if name == "c2" else (None, None)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic_per_launch(F) if args.workload == "c2" else None, "peak_source": peak_src,
-                "kernel": "main fused H->V kernel, one launch per step", "kernel_ms": kernel_ms,
-                "algorithmic_bytes_per_launch": F * ALGO_BYTES_PER_FRAME}
+                "traffic": traffic_pf * F if traffic_pf else None, "traffic_source": traffic_src, "peak_source": peak_src,
+                "kernel": "main fused H->V kernel = the whole step (one launch per step, same flags and content as `value`)",
+                "kernel_ms": ms_local, "algorithmic_bytes_per_launch": F * algo_per_frame,
+                "by_content": {k: v["roofline_frac"] for k, v in by_content.items()}}
     cpu = None
-    if n_gpus == 1 and not args.no_cpu_baseline and args.workload == "c2":
+    if n_gpus == 1 and not args.no_cpu_baseline and name == "c2":
         r = run_reference_cpu(2, 0)
         cpu = {"value": r["value"], "unit": "Mpix/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
     line = {
         "metric": "output Mpix/s", "value": value, "unit": "Mpix/s", "n_gpus": n_gpus, "steps": args.steps,
-        "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong" if name == "c3" else "weak",
         "vs_baseline": None, "dtype": "f32 (f64 exact re-evaluation near integers)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": F, "content": args.content,
-                   "l2": f"inputs larger than L2: {F * ALGO_BYTES_PER_FRAME / 1e6:.0f} MB streamed per GPU per step",
+                   "content_note": "mix = even frames image-like (smooth + noise), odd frames uniform noise; see by_content",
+                   "l2": f"inputs larger than L2: {F * algo_per_frame / 1e6:.0f} MB streamed per GPU per step",
                    "kernel_id": kernel_id, "flags": args.flags},
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "worst_case": worst, "tolerance_mode": tol,
+        "by_content": by_content,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "tolerance_mode": tol,
         "single_frame_launches": single,
         "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
     }
+    line.update(extra)
     print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    ctx.close()
 
 
 if __name__ == "__main__":
