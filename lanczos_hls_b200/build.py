@@ -57,7 +57,11 @@ def _hash(files, flags):
 
 
 def _compile_one(src, flags, objdir, verbose):
-    key = _hash([src] + _headers(), flags)
+    deps = [src] + _headers()
+    with open(src) as fh:
+        if '#include "lanczos_' in fh.read():      # a translation unit that includes another .cu (lanczos_dyn2.cu)
+            deps += [f for f in _sources() if f != src]
+    key = _hash(deps, flags)
     obj = os.path.join(objdir, os.path.basename(src) + ".o")
     stamp = obj + ".stamp"
     if os.path.exists(obj) and os.path.exists(stamp):

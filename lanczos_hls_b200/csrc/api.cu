@@ -92,6 +92,21 @@ struct StreamLease {
 // pitch is the row size rounded up to 16 bytes (what the TMA kernels want).  Only the pixels of a row are
 // touched on either side: padding bytes of the caller's buffer are neither read nor written.
 long long scratch_pitch(long long row_bytes) { return (row_bytes + 15) / 16 * 16; }
+
+// The host drivers own their device buffers, so they may run the kernels on a WIDENED image: input and output
+// widths rounded up until a row is a whole number of 32-bit words (what the TMA kernels need), the extra input
+// columns zero.  A zero column is the reference's dropped tap (full_TB.h:59: taps outside the row are skipped,
+// no renormalisation) and every output column is computed independently of the others, so the original columns
+// come out bit for bit; the extra output columns are never copied back.  The reference's own sample size
+// (lanczos.h:13-14: 162 -> 486 pixels, planar) takes the specialised kernels this way.
+lanczos_desc widened(const lanczos_desc &r) {
+    lanczos_desc d = r;            // resolved: scale_n / scale_d are explicit, so the ratio does not follow the new widths
+    const int q = d.channels == 4 ? 1 : (d.channels == 2 ? 2 : 4);
+    d.in_w = (r.in_w + q - 1) / q * q;
+    d.out_w = (r.out_w + q - 1) / q * q;
+    d.in_pitch = d.out_pitch = 0;
+    return d;
+}
 cudaError_t copy_rows(void *dst, long long dpitch, const void *src, long long spitch, long long row_bytes, long long rows,
                       cudaMemcpyKind kind, cudaStream_t s) {
     if (rows <= 0) return cudaSuccess;
@@ -607,14 +622,17 @@ int lanczos_b200_upscale_host(const lanczos_desc *desc, const uint8_t *h_in, uin
     if (n_frames < 0) return LANCZOS_ERR_DIMS;
     DeviceGuard g(device);
     if (!g.ok) return cuda_fail(cudaErrorInvalidDevice, "cudaSetDevice");
+    lanczos_desc user;
+    int rc = resolve_desc(desc, &user);
+    if (rc != LANCZOS_OK) return rc;
+    const lanczos_desc wide = widened(user);
+    const bool is_wide = wide.in_w != user.in_w || wide.out_w != user.out_w;
     std::shared_ptr<DevicePlan> dp;
-    int rc = get_plan(desc, device, &dp);
+    rc = get_plan(&wide, device, &dp);
     if (rc != LANCZOS_OK) return rc;
     const Plan &h = dp->host();
-    lanczos_desc user;
-    resolve_desc(desc, &user);
-    const long long in_row = (long long)h.d.in_w * h.d.channels, out_row = (long long)h.d.out_w * h.d.channels;
-    const long long d_in_pitch = scratch_pitch(in_row), d_out_pitch = scratch_pitch(out_row);
+    const long long in_row = (long long)user.in_w * user.channels, out_row = (long long)user.out_w * user.channels;
+    const long long d_in_pitch = scratch_pitch((long long)wide.in_w * wide.channels), d_out_pitch = scratch_pitch((long long)wide.out_w * wide.channels);
     if (in_frame_stride == 0) in_frame_stride = user.in_pitch * h.d.in_h;
     if (out_frame_stride == 0) out_frame_stride = user.out_pitch * h.d.out_h;
     if (n_streams < 1) n_streams = 3;
@@ -651,6 +669,7 @@ int lanczos_b200_upscale_host(const lanczos_desc *desc, const uint8_t *h_in, uin
         bin[i].reset(new Scratch(device, max_in));
         bout[i].reset(new Scratch(device, max_out));
         if (!bin[i]->p || !bout[i]->p) return LANCZOS_ERR_NOMEM;
+        if (is_wide) CU(cudaMemsetAsync(bin[i]->p, 0, max_in, streams[i].s));   // the extra columns stay zero: only pixels are copied in
     }
     int64_t launches = 0;
     for (size_t k = 0; k < items.size(); k++) {
@@ -678,8 +697,10 @@ int lanczos_b200_upscale_host_bands(const lanczos_desc *desc, const uint8_t *h_i
     lanczos_desc user;
     int rc = resolve_desc(desc, &user);
     if (rc != LANCZOS_OK) return rc;
+    const lanczos_desc wide = widened(user);
+    const bool is_wide = wide.in_w != user.in_w || wide.out_w != user.out_w;
     const long long in_row = (long long)user.in_w * user.channels, out_row = (long long)user.out_w * user.channels;
-    const long long d_in_pitch = scratch_pitch(in_row), d_out_pitch = scratch_pitch(out_row);
+    const long long d_in_pitch = scratch_pitch((long long)wide.in_w * wide.channels), d_out_pitch = scratch_pitch((long long)wide.out_w * wide.channels);
     std::vector<int> rcs(n_devices, LANCZOS_OK);
     std::vector<std::string> errs(n_devices);
     std::vector<int64_t> launches(n_devices, 0);
@@ -694,7 +715,7 @@ int lanczos_b200_upscale_host_bands(const lanczos_desc *desc, const uint8_t *h_i
                 DeviceGuard g(dev);
                 if (!g.ok) return cuda_fail(cudaErrorInvalidDevice, "cudaSetDevice");
                 std::shared_ptr<DevicePlan> dp;
-                int rc2 = get_plan(desc, dev, &dp);
+                int rc2 = get_plan(&wide, dev, &dp);
                 if (rc2 != LANCZOS_OK) return rc2;
                 int in0, inn;
                 band_rows(dp->host(), r0, r1 - r0, &in0, &inn);
@@ -702,6 +723,7 @@ int lanczos_b200_upscale_host_bands(const lanczos_desc *desc, const uint8_t *h_i
                 if (!bin.p || !bout.p) return LANCZOS_ERR_NOMEM;
                 StreamLease st;   // after the scratch buffers: synchronised before they are released
                 CU(st.acquire(dev));
+                if (is_wide) CU(cudaMemsetAsync(bin.p, 0, (size_t)(inn * d_in_pitch), st.s));
                 CU(copy_rows(bin.p, d_in_pitch, h_in + (long long)in0 * user.in_pitch, user.in_pitch, in_row, inn,
                              cudaMemcpyHostToDevice, st.s));
                 rc2 = run_device(*dp, desc->flags, (const uint8_t *)bin.p, (uint8_t *)bout.p, 1, 0, 0, r0,
@@ -742,13 +764,19 @@ int lanczos_b200_expected(const lanczos_desc *desc, const uint8_t *h_in_planar, 
     // planes stay planes: each one is upscaled as a one-channel frame (no interleaving round trip); on the device
     // the rows of a plane are padded to 16 bytes so that odd widths keep the TMA kernels
     const long long planes = r.channels;
-    const long long d_in_pitch = scratch_pitch(r.in_w), d_out_pitch = scratch_pitch(r.out_w);
+    lanczos_desc plane = r;
+    plane.channels = 1;
+    const lanczos_desc wide = widened(plane);               // one-channel planes: widths rounded up to 4 pixels
+    const long long d_in_pitch = scratch_pitch(wide.in_w), d_out_pitch = scratch_pitch(wide.out_w);
+    d = wide;
+    d.channels = r.channels;
     d.in_pitch = d_in_pitch;
     d.out_pitch = d_out_pitch;
     Scratch pin(device, (size_t)(d_in_pitch * r.in_h * planes)), pout(device, (size_t)(d_out_pitch * r.out_h * planes));
     if (!pin.p || !pout.p) return LANCZOS_ERR_NOMEM;
     StreamLease st;
     CU(st.acquire(device));
+    if (wide.in_w != r.in_w) CU(cudaMemsetAsync(pin.p, 0, (size_t)(d_in_pitch * r.in_h * planes), st.s));
     CU(copy_rows(pin.p, d_in_pitch, h_in_planar, r.in_w, r.in_w, (long long)r.in_h * planes, cudaMemcpyHostToDevice, st.s));
     rc = lanczos_b200_upscale_planar(&d, (const uint8_t *)pin.p, (uint8_t *)pout.p, 1, 0, 0, device, st.s);
     if (rc != LANCZOS_OK) return rc;

@@ -57,7 +57,7 @@ struct GeoD {
     static constexpr int SWB = 32 * VB;                  // strip width in output bytes = ring pitch
     static constexpr int TAPS = 2 * A;
     static constexpr int U = lcm2d(D);                   // input rows per V loop iteration (one ratio period, even)
-    static constexpr int RB = U * cdivd(6, U);           // input rows per chunk
+    static constexpr int RB = U * cdivd(TAPS > 6 ? TAPS : 6, U);   // input rows per chunk (>= 2a - 1: see the ring)
     static constexpr int REGIONS = 2;
     static constexpr int RING = REGIONS * RB;
     static constexpr int STAGES = 4;
@@ -593,7 +593,17 @@ int launch_dyn_one(const KParams &k, const FastHostTables &t, cudaStream_t s) {
 }  // namespace
 
 // Returns 0 on launch, >0 cudaError, -1 when no instance applies (caller falls back to the generic kernel).
+// The instances are split over two translation units (lanczos_dyn.cu: LZD_PART 0, lanczos_dyn2.cu: LZD_PART 1)
+// so that they compile in parallel.
+#ifndef LZD_PART
+#define LZD_PART 0
+#endif
+#if LZD_PART == 0
+int launch_dyn_part1(const KParams &k, const FastHostTables &t, int *kernel_id, cudaStream_t s);
 int launch_dyn(const KParams &k, const FastHostTables &t, int *kernel_id, cudaStream_t s) {
+#else
+int launch_dyn_part1(const KParams &k, const FastHostTables &t, int *kernel_id, cudaStream_t s) {
+#endif
     if ((k.in_w * k.channels) % 4 != 0 || (k.out_w * k.channels) % 4 != 0) return -1;
     if (k.in_pitch % 16 != 0 || k.out_pitch % 4 != 0) return -1;
     if ((reinterpret_cast<uintptr_t>(k.in) & 15) != 0 || (reinterpret_cast<uintptr_t>(k.out) & 3) != 0) return -1;
@@ -606,12 +616,31 @@ int launch_dyn(const KParams &k, const FastHostTables &t, int *kernel_id, cudaSt
         *kernel_id = id;                                                            \
         return mode == 0 ? launch_dyn_one<c, a, n, d, 0>(k, t, s) : launch_dyn_one<c, a, n, d, 1>(k, t, s); \
     }
+#if LZD_PART == 0
     LZD_CASE(3, 3, 17, 10, 5)
     LZD_CASE(3, 3, 3, 2, 6)
     LZD_CASE(3, 3, 3, 1, 7)
     LZD_CASE(1, 3, 17, 10, 11)
-#undef LZD_CASE
+    // the reference author's own sample configuration (lanczos.h:13-28: 162x89 -> 486x267, 3x, LANCZOS_A 2): interleaved
+    // RGB, and one-channel planes (the layout of lanczos_expected itself, through lanczos_b200_upscale_planar / _expected)
+    LZD_CASE(3, 2, 3, 1, 12)
+    LZD_CASE(1, 2, 3, 1, 13)
+    LZD_CASE(3, 3, 4, 1, 14)
+    LZD_CASE(1, 3, 3, 1, 15)
+    return launch_dyn_part1(k, t, kernel_id, s);
+#else
+    LZD_CASE(3, 3, 5, 3, 16)
+    LZD_CASE(3, 3, 7, 4, 17)
+    LZD_CASE(2, 3, 2, 1, 18)
+    LZD_CASE(3, 4, 2, 1, 19)
+    LZD_CASE(3, 1, 2, 1, 20)
+    LZD_CASE(4, 3, 3, 1, 21)
+    LZD_CASE(4, 3, 4, 1, 22)
+    LZD_CASE(3, 2, 3, 2, 23)
+    LZD_CASE(1, 3, 4, 1, 24)
     return -1;
+#endif
+#undef LZD_CASE
 }
 
 }  // namespace lzb
