@@ -44,6 +44,13 @@ def lib():
         L.oracle_fnv1a64.restype = C.c_uint64
         L.oracle_hls_lut.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]
         L.oracle_hls_upscale.argtypes = [u8p, u8p] + [C.c_int] * 8
+        i32p = C.POINTER(C.c_int32)
+        L.oracle_hls_mac1.argtypes = [u8p, i32p, C.c_int, C.c_int]
+        L.oracle_hls_mac1.restype = C.c_int32
+        L.oracle_hls_mac2.argtypes = [i32p, i32p, C.c_int, C.c_int]
+        L.oracle_hls_mac2.restype = C.c_int32
+        L.oracle_hls_to_byte.argtypes = [C.c_int32, C.c_int]
+        L.oracle_hls_to_byte.restype = C.c_uint8
         _lib = L
     return _lib
 
@@ -156,3 +163,18 @@ def hls_upscale(img, n, a=3, bp=8):
     if lib().oracle_hls_upscale(_p(img), _p(out), c, w, h, w * n, h * n, a, n, bp) != 0:
         raise ValueError("oracle rejected the HLS arguments")
     return out
+
+
+def ref_hls_path(a, bp):
+    return os.path.join(HERE, "_ref", "libref_hls_a%d_c3_bp%d.so" % (a, bp))
+
+
+def ref_hls_lib(a, bp):
+    """The reference's own compute / compute_ / clamp_to_byte (worker.cpp:10-130) compiled against oracle/ap_shim.h."""
+    L = C.CDLL(ref_hls_path(a, bp))
+    u8p, i32p = C.POINTER(C.c_uint8), C.POINTER(C.c_int32)
+    L.ref_hls_compute.argtypes = [u8p, i32p, i32p]
+    L.ref_hls_compute2.argtypes = [i32p, i32p, i32p]
+    L.ref_hls_clamp_to_byte.argtypes = [i32p, u8p]
+    L.ref_hls_config.argtypes = [i32p]
+    return L

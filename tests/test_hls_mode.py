@@ -71,3 +71,66 @@ def test_gpu_hls_batch_and_errors(lz, oracle):
     with pytest.raises(lz.LanczosError) as e:
         lz.upscale_hls_device(d_in[0], bad)
     assert e.value.code == -5
+
+
+@pytest.mark.parametrize("cfg", [(3, 8), (2, 8), (3, 6), (3, 10)], ids=lambda c: "a%d_bp%d" % c)
+def test_sample_arithmetic_against_compiled_reference(oracle, cfg):
+    """The pin of the fixed-point path: oracle/hls_oracle.c's per-sample arithmetic against the reference's OWN
+    compute / compute_ / clamp_to_byte (worker.cpp:45-130), compiled as they are against the integer-backed
+    ap_fixed / ap_uint stand-ins of oracle/ap_shim.h (oracle/Makefile target refhls).  Windows: random bytes, flat
+    runs, extremes; kernels: every phase of the LUT for 2x..5x, and random kernel_t values small enough that the
+    10 integer bits of num_el_t cannot wrap, plus a few that do (AP_WRAP is part of the restatement)."""
+    import ctypes as C
+    import os
+    a, bp = cfg
+    if not os.path.exists(oracle.ref_hls_path(a, bp)):
+        pytest.skip("oracle/_ref/libref_hls_* not built (no reference tree)")
+    R = oracle.ref_hls_lib(a, bp)
+    L = oracle.lib()
+    got = (C.c_int32 * 3)()
+    R.ref_hls_config(got)
+    assert list(got) == [3, a, bp]
+    rng = np.random.default_rng(a * 100 + bp)
+    taps = 2 * a
+    kernels = []
+    for n in (2, 3, 4, 5):
+        lut = oracle.hls_lut(a, n, bp)
+        for ph in range(n):                      # output x = base*n + ph: weights LUT[|ph - (j - a + 1) * n|]
+            kernels.append(np.array([lut[abs(ph - (j - a + 1) * n)] for j in range(taps)], np.int32))
+    for _ in range(40):
+        kernels.append(rng.integers(-(1 << bp) // 3, (1 << bp) // 3, size=taps).astype(np.int32))
+    for _ in range(10):
+        kernels.append(rng.integers(-(1 << (bp + 2)), 1 << (bp + 2), size=taps).astype(np.int32))   # wraps
+    i32p, u8p = C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
+    n_cases = 0
+    for k in kernels:
+        kp = k.ctypes.data_as(i32p)
+        for trial in range(60):
+            win = rng.integers(0, 256, size=(taps, 3)).astype(np.uint8)
+            if trial % 6 == 1:
+                win[:] = rng.integers(0, 256)
+            elif trial % 6 == 2:
+                win[:] = rng.choice([0, 255], size=(taps, 3))
+            out = np.zeros(3, np.int32)
+            R.ref_hls_compute(win.ctypes.data_as(u8p), kp, out.ctypes.data_as(i32p))
+            mine = [L.oracle_hls_mac1(np.ascontiguousarray(win[:, c]).ctypes.data_as(u8p), kp, a, bp) for c in range(3)]
+            assert out.tolist() == mine, (k.tolist(), win.tolist())
+            # second pass: fixed-point intermediates as the first pass produces them (>= 0, < 256), and raw extremes
+            mid = rng.integers(0, 256 << bp, size=(taps, 3)).astype(np.int32)
+            if trial % 6 == 3:
+                mid[:] = rng.integers(0, 256 << bp)
+            out2 = np.zeros(3, np.int32)
+            R.ref_hls_compute2(mid.ctypes.data_as(i32p), kp, out2.ctypes.data_as(i32p))
+            mine2 = [L.oracle_hls_mac2(np.ascontiguousarray(mid[:, c]).ctypes.data_as(i32p), kp, a, bp) for c in range(3)]
+            assert out2.tolist() == mine2, (k.tolist(), mid.tolist())
+            b = np.zeros(3, np.uint8)
+            R.ref_hls_clamp_to_byte(out2.ctypes.data_as(i32p), b.ctypes.data_as(u8p))
+            assert b.tolist() == [L.oracle_hls_to_byte(int(v), bp) for v in out2]
+            n_cases += 3
+    # clamp_to_byte on its whole domain, negative values included
+    for raw in list(range(-(512 << bp), 512 << bp, 37)) + [-1, 0, 1, (256 << bp) - 1, 256 << bp]:
+        v = np.array([raw, raw, raw], np.int32)
+        b = np.zeros(3, np.uint8)
+        R.ref_hls_clamp_to_byte(v.ctypes.data_as(i32p), b.ctypes.data_as(u8p))
+        assert b[0] == L.oracle_hls_to_byte(raw, bp), raw
+    assert n_cases > 10000
