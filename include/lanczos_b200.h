@@ -72,7 +72,14 @@ enum {
      * plain fp32 without the exact re-evaluation of near-integer sums and of integer-aligned rows.
      * Every output byte is within 1 LSB of the reference; the exact-match fraction is reported by
      * bench.py and asserted in tests/ (> 0.999 on image-like content). */
-    LANCZOS_FLAG_TOLERANCE_1LSB = 1u << 3
+    LANCZOS_FLAG_TOLERANCE_1LSB = 1u << 3,
+    /* Device-buffer entry points only: the caller promises that this call reads nothing that earlier work on the same
+     * CUDA stream is still writing (independent frames of a video, one call per frame).  The kernel is then launched
+     * with programmatic dependent launch and does not wait for the previous kernel of the stream, so consecutive
+     * single-frame calls overlap on the GPU like the frames of one batch launch instead of running back to back
+     * (BASELINE configs[1] read literally: one 1080p frame per call).  Later work on the stream still waits for the
+     * call as usual.  Without the flag a call is ordered after everything before it on its stream, like any kernel. */
+    LANCZOS_FLAG_INDEPENDENT = 1u << 4
 };
 
 /* Runtime replacement for the reference's compile-time params.h macros

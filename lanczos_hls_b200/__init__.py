@@ -13,6 +13,7 @@ from .api import (  # noqa: F401
     FLAG_NO_ALIAS,
     FLAG_FAST_ALIGNED,
     FLAG_TOLERANCE_1LSB,
+    FLAG_INDEPENDENT,
     FLAG_GENERIC_KERNEL,
     abi_version,
     alias_rows,

@@ -15,6 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 FLAG_NO_ALIAS = 1 << 0
 FLAG_FAST_ALIGNED = 1 << 1
 FLAG_TOLERANCE_1LSB = 1 << 3
+FLAG_INDEPENDENT = 1 << 4
 FLAG_GENERIC_KERNEL = 1 << 2
 
 

@@ -69,6 +69,7 @@ struct V6Params {
     float guard_h, guard_v;   // rigorous fp32 error bounds (x1.05) of the two summation orders
     int uniform_x, uniform_y; // double weights identical for all coordinates of a phase -> wdtab usable
     int strict_v_identity;    // 0 with LANCZOS_FLAG_FAST_ALIGNED
+    int independent;          // LANCZOS_FLAG_INDEPENDENT: launched with programmatic dependent launch, no wait for the previous kernel
     int alias_rows, alias_top_row;   // in-place top rows done inside this kernel (0 = none / separate kernel)
     float align_k[8];         // phase-0 "cannot flip" constants
     int align_ki[8];          // the same, ceil(K * 2^16), for the integer re-check in the slow paths
@@ -601,6 +602,11 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
     const int tid = threadIdx.x & 31, warp = threadIdx.x >> 5;
     Smem6<G> &sm = reinterpret_cast<Smem6<G> *>(smem_raw)[warp];
     const int strip = blockIdx.x * W + warp, seg = blockIdx.y, frame = blockIdx.z;
+    // programmatic dependent launch: let the next kernel of the stream start as soon as SMs free up; unless the caller
+    // declared the frames independent, wait here until everything before this kernel on the stream has completed
+    // (both are no-ops for a launch without the attribute)
+    asm volatile("griddepcontrol.launch_dependents;");
+    if (!p.independent) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (strip * G::SWV >= p.out_w * C) return;
     uint8_t *out_frame = p.out + (long long)frame * p.out_frame_stride;
 
@@ -1111,6 +1117,20 @@ int launch_v6_one(const KParams &k, const FastHostTables &t, int *alias_in_kerne
     p.strict_counter = k.strict_counter;
 
     dim3 grid((strips + W - 1) / W, segs, k.n_frames);
+    p.independent = (k.flags & LANCZOS_FLAG_INDEPENDENT) ? 1 : 0;
+    if (p.independent) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(32 * W);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr{};
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        return (int)cudaLaunchKernelEx(&cfg, kern, map, p);
+    }
     kern<<<grid, 32 * W, smem, s>>>(map, p);
     return (int)cudaGetLastError();
 }
