@@ -180,9 +180,10 @@ int lanczos_b200_stream(const lanczos_desc *desc, const uint32_t *h_in_words,
  * |out*SCALE_D - in*SCALE_N| (kernel.cpp:50-67), exact integer MAC + de-ring clamp to the two central
  * taps (worker.cpp:45-115), zero borders above/left and replicated borders below/right
  * (worker.cpp:170-198,239-275).  Integer scales only (scale_d == 1, a*scale_n <= 127);
- * bit_precision = BIT_PRECISION (lanczos.h:28), 1..12.  The LUT is floor(L(x)*2^BP) with L in double:
- * the reference's hls::sinpi values are not available, so parity with the reference is UNPINNED;
- * results are bit-exact against oracle/hls_oracle.c.  Device buffers, asynchronous. */
+ * bit_precision = BIT_PRECISION (lanczos.h:28), 1..12.  Results are bit-exact against oracle/hls_oracle.c, whose
+ * per-sample arithmetic is pinned to the reference's own worker.cpp:10-130 (compiled against an integer-backed
+ * ap_fixed shim, oracle/Makefile target refhls).  The LUT is floor(L(x)*2^BP) with L in double: the reference's
+ * hls::sinpi values are not available, so the LUT content is UNPINNED.  Device buffers, asynchronous. */
 int lanczos_b200_upscale_hls(const lanczos_desc *desc, const uint8_t *d_in, uint8_t *d_out,
                              int32_t bit_precision, int32_t n_frames, int64_t in_frame_stride,
                              int64_t out_frame_stride, int device, void *cuda_stream);
