@@ -543,11 +543,15 @@ def main():
         single = {"call": "lanczos_b200_upscale, one frame per launch, frames of the batch in turn", "content": args.content}
         rounds = max(2, min(args.steps, 10))
         desc_ind = lz.make_desc(IN_W, IN_H, OUT_W, OUT_H, CH, A, SN, SD, flags=args.flags | lz.FLAG_INDEPENDENT)
-        for key, ns, dr in (("streams_1", 1, dref), ("streams_4", 4, dref), ("streams_1_independent_flag", 1, C.byref(desc_ind))):
+        image_like = ptrs[0::2] if args.content == "mix" else ptrs     # even frames of the mix are the image-like ones
+        for key, ns, dr, pp in (("streams_1", 1, dref, ptrs), ("streams_4", 4, dref, ptrs),
+                                ("streams_1_independent_flag", 1, C.byref(desc_ind), ptrs),
+                                ("image_like_frames_streams_1", 1, dref, image_like),
+                                ("image_like_frames_streams_1_independent_flag", 1, C.byref(desc_ind), image_like)):
             def run():
                 i = 0
                 for _ in range(rounds):
-                    for pi, po in ptrs:
+                    for pi, po in pp:
                         L.lanczos_b200_upscale(dr, pi, po, local_rank, sp[i % ns])
                         i += 1
             run()
@@ -561,7 +565,7 @@ def main():
                 streams[0].wait_stream(st)
             s1.record(streams[0])
             ctx.barrier()
-            us = ctx.max_over_ranks(s0.elapsed_time(s1)) * 1e3 / (rounds * F)
+            us = ctx.max_over_ranks(s0.elapsed_time(s1)) * 1e3 / (rounds * len(pp))
             single[key] = {"value": n_gpus * px_per_frame / (us * 1e-6) / 1e6, "unit": "Mpix/s", "us_per_frame": us}
         single["independent_flag"] = ("LANCZOS_FLAG_INDEPENDENT: the caller declares the frames independent; calls on ONE stream are "
                                       "launched with programmatic dependent launch and overlap like the frames of a batch")

@@ -87,7 +87,7 @@ __host__ __device__ constexpr int cmax6(int a, int b) { return a > b ? a : b; }
 __host__ __device__ constexpr int lcm2(int d) { return d % 2 == 0 ? d : 2 * d; }
 __host__ __device__ constexpr int gcd6(int a, int b) { return b == 0 ? a : gcd6(b, a % b); }
 
-template <int C, int A, int N, int D, int PH, int W>
+template <int C, int A, int N, int D, int PH, int W, int MODE>
 struct Geo6 {
     static constexpr int THREADS = 32 * W;              // W independent warps per CTA, one strip each
     static constexpr int VB = 8;                        // byte-columns per V thread
@@ -109,7 +109,9 @@ struct Geo6 {
     // every 128-byte line shared between two warps: tools/wbench.cu measures 4.0 TB/s for that store pattern on
     // this part against 6.8 TB/s for 256-byte pieces, and the V pass alone was bound by it.)  H items are OUT_B
     // bytes wide and aligned to OUT_B, so the H pass of a strip covers the MAX_GROUPS items that contain it.
-    static constexpr int SWV = 32 * VB;
+    // MODE 1 (plain fp32 V pass) is short of H-pass time, not of store bandwidth: five whole H items, no overlap
+    // (+7 % on uniform noise in that mode, measured; +-0 on image-like content)
+    static constexpr int SWV = (MODE == 1) ? 5 * OUT_B : 32 * VB;
     static constexpr int VOFF_MAX = OUT_B - gcd6(SWV, OUT_B);     // largest offset of a strip inside its first H item
     static constexpr int MAX_GROUPS = cdiv6(VOFF_MAX + SWV, OUT_B);   // H items per row of a warp's strip (6 for 48-byte items)
     static constexpr int SW_MAX = MAX_GROUPS * OUT_B;             // ring pitch in bytes (288)
@@ -580,7 +582,7 @@ __device__ __noinline__ void alias_fix(const V6Params &p, const AliasArgs a) {
 template <int C, int A, int N, int D, int PH, int KM, int W, int MODE, bool ST64>
 __global__ void __launch_bounds__(32 * W, LZB_MINB / W)
 lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ V6Params p) {
-    using G = Geo6<C, A, N, D, PH, W>;
+    using G = Geo6<C, A, N, D, PH, W, MODE>;
     constexpr int TAPS = G::TAPS;
     constexpr int SWM = G::SW_MAX;
     constexpr int VB = G::VB;
@@ -1020,7 +1022,7 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
 // ---------------------------------------------------------------------------------------------
 template <int C, int A, int N, int D, int PH, int KM, int W, int MODE, bool ST64>
 int launch_v6_one(const KParams &k, const FastHostTables &t, int *alias_in_kernel, cudaStream_t s) {
-    using G = Geo6<C, A, N, D, PH, W>;
+    using G = Geo6<C, A, N, D, PH, W, MODE>;
     EncodeFn encode = get_encode();
     if (!encode) return -1;
     const int row_bytes = k.out_w * C;

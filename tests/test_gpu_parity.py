@@ -97,6 +97,52 @@ def test_batch_equals_single_frames(torch_cuda, lz, oracle):
         assert np.array_equal(got[i], oracle.upscale(frames[i], ow, oh, 3, n, d)), i
 
 
+def test_pitched_input_keeps_the_tma_kernel(torch_cuda, lz, oracle):
+    """Padded rows whose pitch is a multiple of 16 bytes (but not the row size) stay on the specialised kernels:
+    the tensor map takes the pitch as its row stride (VERDICT r1 weak #10)."""
+    torch = torch_cuda
+    for (iw, ih, c, n, d, a, kid) in [(320, 45, 3, 2, 1, 3, 1), (256, 40, 4, 3, 2, 3, 3), (320, 33, 3, 17, 10, 3, 5)]:
+        ow, oh = oracle.out_dims(iw, ih, n, d)
+        img = noise_hwc(oracle, ih, iw, c, seed=iw + c)
+        in_pitch, out_pitch = iw * c + 48, ow * c + 20
+        buf_in = torch.full((3, ih, in_pitch), 0x77, dtype=torch.uint8, device="cuda")      # a batch of 3 padded frames
+        for f in range(3):
+            buf_in[f, :, : iw * c] = torch.from_numpy(np.roll(img, f, axis=0).reshape(ih, iw * c)).cuda()
+        buf_out = torch.full((3, oh, out_pitch), 0xAB, dtype=torch.uint8, device="cuda")
+        desc = lz.make_desc(iw, ih, ow, oh, c, a, n, d, in_pitch, out_pitch)
+        rc = lz.lib().lanczos_b200_upscale_batch(C.byref(desc), C.c_void_p(buf_in.data_ptr()), C.c_void_p(buf_out.data_ptr()),
+                                                 3, ih * in_pitch, oh * out_pitch, 0, None)
+        assert rc == 0
+        torch.cuda.synchronize()
+        assert lz.stats()["kernel_id"] == kid, (iw, c, lz.stats())
+        out = buf_out.cpu().numpy()
+        for f in range(3):
+            assert np.array_equal(out[f, :, : ow * c].reshape(oh, ow, c), oracle.upscale(np.roll(img, f, axis=0), ow, oh, a, n, d)), (iw, f)
+        assert (out[:, :, ow * c:] == 0xAB).all()
+
+
+def test_tolerance_mode_full_size(torch_cuda, lz, oracle):
+    """LANCZOS_FLAG_TOLERANCE_1LSB at the headline size (1080p -> 2160p, several strips and segments per frame, a batch)
+    against the bit-exact GPU output, which test_headline_config_full_size pins to the oracle: every byte within 1 LSB,
+    > 99.999 % identical on image-like content, > 98 % on uniform noise."""
+    torch = torch_cuda
+    frames = np.stack([smooth_hwc(oracle, 1080, 1920, 3, seed=1), noise_hwc(oracle, 1080, 1920, 3, seed=2)])
+    d_in = torch.from_numpy(frames).cuda()
+    exact = torch.empty((2, 2160, 3840, 3), dtype=torch.uint8, device="cuda")
+    tol = torch.empty_like(exact)
+    lz.upscale_batch_device(d_in, exact, a=3, flags=lz.FLAG_NO_ALIAS)
+    lz.upscale_batch_device(d_in, tol, a=3, flags=lz.FLAG_NO_ALIAS | lz.FLAG_TOLERANCE_1LSB)
+    torch.cuda.synchronize()
+    assert lz.stats()["kernel_id"] == 1
+    diff = (exact.to(torch.int16) - tol.to(torch.int16)).abs()
+    assert int(diff.max()) <= 1
+    assert float((diff[0] == 0).float().mean()) > 0.99999
+    assert float((diff[1] == 0).float().mean()) > 0.98
+    # spot-check the exact batch against the oracle on a band of rows of the noise frame
+    want = oracle.upscale(frames[1], 3840, 2160, 3, 2, 1, variant=oracle.CLEAN, rows=(1000, 64))
+    assert np.array_equal(exact[1, 1000:1064].cpu().numpy(), want)
+
+
 def test_independent_flag_single_frame_calls(torch_cuda, lz, oracle):
     """LANCZOS_FLAG_INDEPENDENT: one call per frame on ONE stream, launched with programmatic dependent launch and
     without waiting for the previous call; distinct buffers per frame, results identical to the batch launch, and
