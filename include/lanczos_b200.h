@@ -200,11 +200,15 @@ double lanczos_b200_kernel(double x, int32_t a);
 /* Polyphase table of the plan: `phases` rows of 2a float weights (row p = phase p of the N-periodic
  * ratio, kernel.cpp:40-45's LUT restated per phase). Returns the number of phases or an error. */
 int lanczos_b200_phase_table(const lanczos_desc *desc, float *weights, int32_t capacity_floats);
-/* Introspection for tests: the four fp16x2 constants {-K0, +K1, +K3, -K4} (both lanes equal, times 2^12) of the
- * phase-0 re-check that decides, for an output coordinate exactly on an input sample, whether the reference's
- * double sum (full_TB.h:58-63, weights sin(k*pi)-residues ~1e-17) can fall below the centre value v and truncate
- * to v-1 (a = 3 only; returns 4, or 0 and zeros for other a). tests/test_phase0_filter.py proves the test on CPU. */
-int lanczos_b200_phase0_constants(const lanczos_desc *desc, uint32_t *half2_consts);
+/* Introspection for tests: the five fp32 constants {W0, W1, 1, W3, W4}, W_k = fl32(w_k * 2^29), of the phase-0 second
+ * look.  For an output coordinate exactly on an input sample the reference's double sum (full_TB.h:58-63, weights 1 at
+ * the centre and sin(k*pi) residues ~1e-17 elsewhere) truncates to the centre value v or to v-1; the kernels decide
+ * which with the fp32 chain t = b0*W0, y = fma(b1,W1,t), X = v + y, X = fma(b3,W3,X), X = fma(b4,W4,X), result =
+ * trunc(X), which the plan proves equal to the reference for every (b0,b1,v,b3,b4) by enumerating the states of the
+ * sum (plan.cpp verify_phase0_chain; tests/test_phase0_chain.py repeats the proof in numpy).  Returns 1 when the plan
+ * verified the chain (a = 3), 0 when there is none (other a; the specialised kernels then need no second look or
+ * are not used), or an error. */
+int lanczos_b200_phase0_chain(const lanczos_desc *desc, float *consts5);
 /* Number of top output rows that the reference's in-place pass aliases (0 with NO_ALIAS). */
 int lanczos_b200_alias_rows(const lanczos_desc *desc);
 

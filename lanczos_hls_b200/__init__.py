@@ -26,7 +26,7 @@ from .api import (  # noqa: F401
     lib_path,
     make_desc,
     phase_table,
-    phase0_constants,
+    phase0_chain,
     reduce_ratio,
     resolve,
     stats,

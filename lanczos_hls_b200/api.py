@@ -77,7 +77,7 @@ def lib():
     L.lanczos_b200_kernel.argtypes = [C.c_double, i32]
     L.lanczos_b200_kernel.restype = C.c_double
     L.lanczos_b200_phase_table.argtypes = [dp, C.POINTER(C.c_float), i32]
-    L.lanczos_b200_phase0_constants.argtypes = [dp, C.POINTER(C.c_uint32)]
+    L.lanczos_b200_phase0_chain.argtypes = [dp, C.POINTER(C.c_float)]
     L.lanczos_b200_alias_rows.argtypes = [dp]
     L.lanczos_b200_host_alloc.argtypes = [C.c_size_t]
     L.lanczos_b200_host_alloc.restype = C.c_void_p
@@ -216,11 +216,13 @@ def upscale(img, out_w, out_h, a=3, scale_n=0, scale_d=0, flags=0, device=0, n_s
     return out
 
 
-def phase0_constants(desc):
-    """The fp16x2 constants {-K0, +K1, +K3, -K4} of the slow paths' phase-0 re-check (a = 3), as 4 uint32."""
-    buf = (C.c_uint32 * 4)()
-    _check(lib().lanczos_b200_phase0_constants(C.byref(desc), buf))
-    return [int(v) for v in buf]
+def phase0_chain(desc):
+    """(verified, [W0, W1, 1, W3, W4]) of the plan's exact fp32 phase-0 chain (a = 3), see include/lanczos_b200.h."""
+    buf = (C.c_float * 5)()
+    rc = lib().lanczos_b200_phase0_chain(C.byref(desc), buf)
+    if rc < 0:
+        _check(rc)
+    return bool(rc), [float(v) for v in buf]
 
 
 def bind_host_to_device(device=0):

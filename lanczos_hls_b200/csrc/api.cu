@@ -301,7 +301,8 @@ int run_device(const DevicePlan &dp, unsigned flags, const uint8_t *d_in, uint8_
     int frc = -1;
     if (!(flags & LANCZOS_FLAG_GENERIC_KERNEL)) {
         FastHostTables t{h.phase_w.data(), h.phase_wd.data(), h.align_k.data(), h.x.aligned_exact ? 1 : 0,
-                         h.y.aligned_exact ? 1 : 0, h.x.uniform_phase ? 1 : 0, h.y.uniform_phase ? 1 : 0, h.x.i0.data(), h.p0_half2};
+                         h.y.aligned_exact ? 1 : 0, h.x.uniform_phase ? 1 : 0, h.y.uniform_phase ? 1 : 0, h.x.i0.data(),
+                         h.p0_chain_ok ? h.p0_chain : nullptr};
         frc = launch_v6(p, t, &kid, &alias_done, s);
         if (frc < 0) frc = launch_dyn(p, t, &kid, s);
     }
@@ -431,8 +432,8 @@ int lanczos_b200_phase_table(const lanczos_desc *desc, float *weights, int32_t c
     return d.scale_n;
 }
 
-int lanczos_b200_phase0_constants(const lanczos_desc *desc, uint32_t *half2_consts) {
-    if (!desc || !half2_consts) return LANCZOS_ERR_NULL;
+int lanczos_b200_phase0_chain(const lanczos_desc *desc, float *consts) {
+    if (!desc || !consts) return LANCZOS_ERR_NULL;
     lanczos_desc d = *desc;
     int rc = resolve_desc(desc, &d);
     if (rc != LANCZOS_OK) return rc;
@@ -443,8 +444,8 @@ int lanczos_b200_phase0_constants(const lanczos_desc *desc, uint32_t *half2_cons
     Plan p;
     rc = build_plan(&small, &p);
     if (rc != LANCZOS_OK) return rc;
-    memcpy(half2_consts, p.p0_half2, sizeof(p.p0_half2));
-    return d.a == 3 ? 4 : 0;
+    memcpy(consts, p.p0_chain, sizeof(p.p0_chain));
+    return p.p0_chain_ok ? 1 : 0;
 }
 
 int lanczos_b200_alias_rows(const lanczos_desc *desc) {

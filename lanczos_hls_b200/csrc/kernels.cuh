@@ -39,7 +39,7 @@ struct FastHostTables {            // host-side views of the plan the specialise
     int exact_x, exact_y;          // AxisTables.aligned_exact
     int uniform_x, uniform_y;      // AxisTables.uniform_phase
     const int32_t *i0x_host;       // [out_w] host copy of AxisTables.i0 (x axis)
-    const uint32_t *p0_half2;      // [4] Plan.p0_half2
+    const float *p0_chain;         // [5] Plan.p0_chain, or null when the plan could not verify it
 };
 // Static-phase kernels (lanczos_v6.cu): 8-byte V columns, PRMT-spliced copies, scalar constant-bank FFMA.
 // *alias_in_kernel = 1 when the kernel also produced the in-place top rows (no launch_alias_rows needed).

@@ -48,6 +48,9 @@
 #ifndef LZB_TOL_VU
 #define LZB_TOL_VU 1     // ratio periods per V loop iteration in MODE 1 at D = 1 (2: +2 % on 1080p, -5 % on 4K)
 #endif
+#ifndef LZB_VCOLD_W
+#define LZB_VCOLD_W 4    // byte-columns per pass of the V pass's phase-0 second look (4 or 8)
+#endif
 #ifndef LZB_W
 #define LZB_W 1          // independent warps (strips) per CTA
 #endif
@@ -72,11 +75,9 @@ struct V6Params {
     int independent;          // LANCZOS_FLAG_INDEPENDENT: launched with programmatic dependent launch, no wait for the previous kernel
     int alias_rows, alias_top_row;   // in-place top rows done inside this kernel (0 = none / separate kernel)
     float align_k[8];         // phase-0 "cannot flip" constants
-    int align_ki[8];          // the same, ceil(K * 2^16), for the integer re-check in the slow paths
-    // fp16x2 constants (both lanes equal, times 2^12) of the vectorised phase-0 re-check of the slow paths
-    // (phase0_doubt2): -K of the two negative residues, rounded away from zero; +K of the positive residues
-    // next to the centre, rounded toward zero (0 when the residue is not positive)
-    uint32_t p0_nk0, p0_nk4, p0_k1, p0_k3;
+    // phase-0 second look (a = 3): the reference's double sum restated exactly in fp32 (plan.cpp verify_phase0_chain):
+    // {W0, W1, 1, W3, W4} times 2^24 (the kernels' pixel values carry 2^-24), W_k = fl32(w_k * 2^29)
+    float p0c[5];
     float wtab[32 * 8];       // polyphase table [N][8] (padded to 8 taps), N <= 32, times 2^24
     double wdtab[8 * 8];      // double polyphase table [N][8] for N <= 8 (valid when uniform_*)
     unsigned long long *strict_counter;
@@ -218,44 +219,49 @@ __device__ __forceinline__ uint32_t quantise_f32(float x) {
 // summation order of the H-pass chains: outermost (smallest) weights first, the two central taps last
 template <int TAPS> __host__ __device__ constexpr int tap_order6(int i) { return (i & 1) ? TAPS - 1 - i / 2 : i / 2; }
 
-__device__ __forceinline__ uint32_t hmul2_u(uint32_t a, uint32_t b) {
-    uint32_t d;
-    asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-    return d;
-}
 __device__ __forceinline__ uint32_t hfma2_u(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t d;
     asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
 
-// Vectorised phase-0 re-check of the slow paths (a = 3: negative residues at taps 0 and 4, taps 1 and 3 positive).
-// Inputs: fp16x2 words with the bytes of taps 0, 1, 2 (centre v), 3, 4 as fp16 subnormals (byte * 2^-24).
-// Returns a word whose lane sign bits (0x8000 per lane) are set where the reference MAY return v - 1; a clear
-// bit proves that it returns v.  With H = 2^ceil(log2 v) (half the spacing of doubles below v is H * 2^-54,
-// fast_common.cuh phase0_safe) and K_k = |w_k| * 2^54, the running double sum of full_TB.h:58-63
-//   * is >= v after the centre tap if K_0 b_0 - K_1 b_1 <= H  (the two residues before the centre are added to
-//     each other first, the positive one offsets the negative one), and then
-//   * stays >= v if K_4 b_4 <= H, or if K_3 b_3 - K_4 b_4 >= 2H: tap 3 lifts the sum by at least
-//     K_3 b_3 - H' (H' = half the spacing ABOVE v <= 2H in these units) before tap 4 pulls it down.
-// Every test is one or two HFMA2: a single fp16 FMA rounds once and never changes the sign; where two are
-// chained, the constant of the second has 2^-10 of slack for the rounding of the first (host side).  The
-// constants carry the 0.99 margin of plan.cpp for the rounding of the reference's own products.
-__device__ __forceinline__ uint32_t phase0_doubt2(uint32_t b0, uint32_t b1, uint32_t v, uint32_t b3, uint32_t b4,
-                                                  uint32_t nk0, uint32_t k1, uint32_t k3, uint32_t nk4) {
-    const uint32_t v12 = hmul2_u(v, 0x6C006C00u);                      // v * 2^-12 (4096: exact)
-    const uint32_t t = hfma2_u(v12, 0x40004000u, 0x8C008C00u);         // (2v - 1) * 2^-12, exact
-    const uint32_t H = t & 0x7C007C00u;                                // 2^floor(log2(2v-1)) = H(v), times 2^-12 (v = 0: as v = 1)
-    const uint32_t nH2 = hmul2_u(H, 0xC000C000u);                      // -2H
-    const uint32_t zpre = hfma2_u(b1, k1, hfma2_u(b0, nk0, H));
-    const uint32_t z1 = hfma2_u(b4, nk4, H);
-    const uint32_t z2 = hfma2_u(b3, k3, hfma2_u(b4, nk4, nH2));
-    return (zpre | (z1 & z2)) & 0x80008000u;
+// Phase-0 second look (a = 3): the reference's double sum b0*w0 + b1*w1 + v + b3*w3 + b4*w4 (full_TB.h:58-63 /
+// :71-75 at a coordinate that falls on an input sample; ascending taps, tap 5 never changes it) restated in fp32.
+// The grid of floats around the integer v is the grid of doubles scaled by 2^29, so the sum with residues scaled by
+// 2^29 rounds the way the reference's does at every step; plan.cpp verify_phase0_chain enumerates every reachable
+// state of the sum to prove that the fp32 rounding of the scaled residues never changes a decision (kernels with a
+// phase-0 test are not launched otherwise).  x[k] = the five bytes * 2^-24 (two samples), pc = V6Params.p0c.
+// The truncation of the result is the reference's output: v, or v - 1 when the negative residues win.
+__device__ __forceinline__ float2 phase0_chain2(const float2 (&x)[5], const float *pc) {
+    float2 s = __fmul2_rn(x[0], make_float2(pc[0], pc[0]));
+#pragma unroll
+    for (int k = 1; k < 5; k++) s = __ffma2_rn(x[k], make_float2(pc[k], pc[k]), s);
+    return s;
+}
+// fp32 multiply / FMA WITHOUT .ftz whatever the compilation flags say (a denormal operand must not be flushed)
+__device__ __forceinline__ float fmul_keep_denormals(float a, float b) {
+    float d;
+    asm("mul.rn.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+    return d;
+}
+__device__ __forceinline__ float fma_keep_denormals(float a, float b, float c) {
+    float d;
+    asm("fma.rn.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ float phase0_chain1(const float (&x)[5], const float *pc) {
+    float s = __fmul_rn(x[0], pc[0]);
+#pragma unroll
+    for (int k = 1; k < 5; k++) s = __fmaf_rn(x[k], pc[k], s);
+    return s;
 }
 
-// bit 7 of byte e (e = 0..3) -> bit e
-__device__ __forceinline__ uint32_t sign4_to_bits(uint32_t x) {
-    return ((((x >> 7) & 0x01010101u) * 0x01020408u) >> 24) & 0xfu;
+// Shared-memory loads by 32-bit shared address: the slow paths are out of line, where a generic pointer
+// would turn every access into a generic LD.
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -267,38 +273,85 @@ struct HFixArgs {
     uint8_t *ring_row;        // ring row of the item
     int gbyte0;               // strip-relative output byte of the item's first byte
     int obyte0, ibyte0, valid_bytes;
-    uint32_t fix_g, fix_z;
+    uint32_t fix_g;           // bit per packed word of interpolated samples
+    uint32_t fix_z;           // some phase-0 sample of the item may flip
     float guard;
 };
 
-template <int C, int A, int N, int D, int PH, int KM, int PAD_L>
+template <class G, int C, int A, int N, int D, int PH, int KM>
 __device__ __noinline__ int h_fix(const V6Params &p, const HFixArgs a) {
     constexpr int TAPS = 2 * A;
     constexpr int NI = PH * (N - 1) * C;
-    // vectorised phase-0 re-check: written for a = 3 (residues of taps 0 and 4 negative) and layouts whose
-    // phase-0 centres are whole words
-    constexpr bool VEC0 = (A == 3) && (KM == 0x11) && (D == 1 || C == 4) && ((PH * C) % 4 == 0) && (PH * C <= 32) && (2 * C <= 8);
+    constexpr int PAD_L = G::PAD_L;
     int n_strict = 0;
-    auto fix_byte = [&](int b, bool is_copy) {
+    if constexpr (KM != 0) {
+        if (a.fix_z) {
+            // All phase-0 samples of the item again with the exact fp32 chain (phase0_chain2: the reference's double
+            // sum restated, v or v - 1): the item's window as the hot path reads it, the results spliced over the
+            // copies in the ring row.
+            static_assert(A == 3, "written for the +-2 residues of a = 3");
+            // Register-light (this function is called with the V pass's partial sums live in the caller, see
+            // v_fix_phase0_chunk): the window bytes are taken one after the other, each feeding the sums of the up to
+            // five samples it is a tap of, so only the sums of ~4C + 1 samples are alive at any time.  A byte loaded with
+            // LDS.U8 is, read as fp32, the denormal b * 2^-149, and FFMA takes denormal operands at full rate: with the
+            // constants times 2^101 the chain runs on b * 2^-24 like the hot path's values do (every intermediate a
+            // normal number, so the same roundings), then one exact multiplication by 2^24.
+            const uint32_t t0 = smem_u32(a.in_row) + G::WIN0 + (a.gbyte0 / G::OUT_B) * G::IN_B + G::MIS;    // tap 0 of sample (0, 0)
+            const uint32_t dst = smem_u32(a.ring_row);
+            float kd[5];
+#pragma unroll
+            for (int k = 0; k < 5; k++) kd[k] = p.p0c[k] * 2.535301200456459e30f;       // 2^101, exact
+            constexpr int NBYTES = (PH - 1) * D * C + C + 4 * C;       // window bytes the phase-0 samples of the item touch
+            float sum[PH * C];
+            float fin[4];
+            int fpos[4];
+            int nfin = 0;
+#pragma unroll
+            for (int i = 0; i < NBYTES; i++) {
+                const float x = __uint_as_float(lds_u8(t0 + i));
+#pragma unroll
+                for (int k = 0; k < 5; k++) {
+                    const int sb = i - k * C;                              // tap-0 byte of the sample this byte is tap k of
+                    if (sb < 0 || (sb / C) % D != 0 || (sb / C) / D >= PH) continue;
+                    const int sidx = ((sb / C) / D) * C + sb % C;
+                    if (k == 0) sum[sidx] = fmul_keep_denormals(x, kd[0]);
+                    else sum[sidx] = fma_keep_denormals(x, kd[k], sum[sidx]);
+                    if (k == 4) {
+                        fin[nfin] = sum[sidx] * 16777216.f;
+                        fpos[nfin] = ((sb / C) / D) * N * C + sb % C;    // output byte of the sample inside the item
+                        nfin++;
+                    }
+                }
+                if (nfin == 4 || (i == NBYTES - 1 && nfin > 0)) {
+                    const uint32_t q = quantise4(fin[0], nfin > 1 ? fin[1] : 0.f, nfin > 2 ? fin[2] : 0.f, nfin > 3 ? fin[3] : 0.f);
+                    if (nfin == 4 && fpos[0] % 4 == 0 && fpos[1] == fpos[0] + 1 && fpos[2] == fpos[0] + 2 && fpos[3] == fpos[0] + 3) {
+                        asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst + fpos[0]), "r"(q) : "memory");
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; e++)
+                            if (e < nfin) asm volatile("st.shared.u8 [%0], %1;" ::"r"(dst + fpos[e]), "r"(q >> (8 * e)) : "memory");
+                    }
+                    nfin = 0;
+                }
+            }
+        }
+    }
+    auto fix_byte = [&](int b) {
         if (a.gbyte0 + b >= a.valid_bytes) return;
         const int ob = a.obyte0 + a.gbyte0 + b;                  // global output byte column
         const int xx = ob / C, c = ob - xx * C;
         const int first = (xx * D) / N - A + 1;                  // first tap pixel (full_TB.h:59)
         const int ph = (xx * D) % N;
         const uint8_t *tap0 = a.in_row + PAD_L + first * C + c - a.ibyte0;
-        if (is_copy) {
-            if (VEC0 ? tap0[(A - 1) * C] == 0 : phase0_safe<TAPS, KM>(tap0, C, p.align_ki)) return;
-        } else {
-            // the hot path's fp32 chain again (same order, same weights: same bits): only a sample whose
-            // truncation really is in doubt needs the double evaluation
-            float acc = -a.guard;
+        // the hot path's fp32 chain again (same order, same weights: same bits): only a sample whose
+        // truncation really is in doubt needs the double evaluation
+        float acc = -a.guard;
 #pragma unroll
-            for (int i = 0; i < TAPS; i++) {
-                const int k = tap_order6<TAPS>(i);
-                acc = fmaf((float)tap0[k * C] * (1.f / 16777216.f), p.wtab[ph * 8 + k], acc);
-            }
-            if (quantise_f32(acc) == quantise_f32(acc + 2.f * a.guard)) return;
+        for (int i = 0; i < TAPS; i++) {
+            const int k = tap_order6<TAPS>(i);
+            acc = fmaf((float)tap0[k * C] * (1.f / 16777216.f), p.wtab[ph * 8 + k], acc);
         }
+        if (quantise_f32(acc) == quantise_f32(acc + 2.f * a.guard)) return;
         uint8_t r;
         if (p.uniform_x && N <= 8) r = exact_taps<TAPS>(tap0, C, [&](int k) { return p.wdtab[ph * 8 + k]; });
         else r = exact_taps<TAPS>(tap0, C, [&](int k) { return p.wdx[(long long)xx * TAPS + k]; });
@@ -313,66 +366,12 @@ __device__ __noinline__ int h_fix(const V6Params &p, const HFixArgs a) {
             const int s = 4 * dw + e;
             if (s >= NI) break;
             const int per = s / ((N - 1) * C), rem = s - per * ((N - 1) * C);
-            fix_byte((per * N + 1) * C + rem, false);
-        }
-    }
-    if (a.fix_z) {
-        if constexpr (VEC0) {
-            // all phase-0 samples of the item at once (phase0_doubt2, fp16x2): centre bytes are the item's own
-            // input bytes (D = 1) or the first pixel of every period (C = 4: whole words), tap k lies (k - 2) * C
-            // bytes away.  The item's input starts 8-byte aligned at in_row + PAD_L + g * IN_B.
-            constexpr int IN_B = PH * D * C, NCW = PH * C / 4, CSTEP = (C == 4) ? 4 * D : 4, NLW = (IN_B + 16) / 4;
-            const uint2 *src = reinterpret_cast<const uint2 *>(a.in_row + PAD_L + (a.gbyte0 / (N * C)) * (D * C) - 8);
-            uint32_t lw[NLW];
-#pragma unroll
-            for (int i = 0; i < NLW / 2; i++) {
-                const uint2 w = src[i];
-                lw[2 * i] = w.x;
-                lw[2 * i + 1] = w.y;
-            }
-            uint32_t doubt = 0;       // bit s: phase-0 sample s = per * C + c of the item
-#pragma unroll
-            for (int j = 0; j < NCW; j++) {
-                uint32_t lo[5], hi[5];
-#pragma unroll
-                for (int k = 0; k < 5; k++) {
-                    const int off = 8 + j * CSTEP + (k - 2) * C;        // byte offset of tap k of the word's first sample
-                    const uint32_t w = (off % 4 == 0) ? lw[off / 4] : __byte_perm(lw[off / 4], lw[off / 4 + 1], 0x3210u + 0x1111u * (off % 4));
-                    lo[k] = __byte_perm(w, 0u, 0x4140);
-                    hi[k] = __byte_perm(w, 0u, 0x4342);
-                }
-                const uint32_t dlo = phase0_doubt2(lo[0], lo[1], lo[2], lo[3], lo[4], p.p0_nk0, p.p0_k1, p.p0_k3, p.p0_nk4);
-                const uint32_t dhi = phase0_doubt2(hi[0], hi[1], hi[2], hi[3], hi[4], p.p0_nk0, p.p0_k1, p.p0_k3, p.p0_nk4);
-                doubt |= sign4_to_bits(__byte_perm(dlo, dhi, 0x7531)) << (4 * j);
-            }
-#pragma unroll 1
-            for (; doubt; doubt &= doubt - 1) {
-                const int sidx = __ffs(doubt) - 1;
-                const int per = sidx / C, c = sidx - per * C;
-                fix_byte(per * N * C + c, true);
-            }
-        } else {
-#pragma unroll 1
-            for (int per = 0; per < PH; per++)
-#pragma unroll 1
-                for (int c = 0; c < C; c++) fix_byte(per * N * C + c, true);
+            fix_byte((per * N + 1) * C + rem);
         }
     }
     return n_strict;
 }
 
-// Shared-memory loads by 32-bit shared address: the slow paths are out of line, where a generic pointer
-// would turn every access into a generic LD.
-__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint2 lds_v2(uint32_t a) {
-    uint2 v;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
-    return v;
-}
 // bit 0 of byte e (e = 0..3) -> bit e
 __device__ __forceinline__ uint32_t lsb4_to_bits(uint32_t x) {
     return (((x & 0x01010101u) * 0x01020408u) >> 24) & 0xfu;
@@ -408,10 +407,9 @@ template <int A, int N, int D, int VU, int S0> __host__ __device__ constexpr int
     for (int u = 0; u < VU; u++) n += ((S0 + u + A) % D == 0) ? 1 : 0;
     return n;
 }
-template <int NI, int NZ>
+template <int NI>
 struct VIterFlags {
     uint32_t dx[NI > 0 ? NI : 1], dy[NI > 0 ? NI : 1];   // interpolated rows of the iteration, in the order they complete
-    uint32_t zr[NZ > 0 ? NZ : 1];                         // phase-0 rows of the iteration
 };
 
 // bytes of an interpolated row: NT = 2a taps from ring slots slot0 .. (ascending rows = ascending taps)
@@ -436,56 +434,78 @@ __device__ __forceinline__ int fix_interp_bytes(const V6Params &p, uint32_t col,
     return n;
 }
 
-// bytes of a phase-0 row (copy of ring row c): the sharper vectorised test (phase0_doubt2) on all 8 bytes, then the
-// reference's double sum for what is still in doubt.  Runs when row c + 2 has arrived, i.e. with taps 0..4 (rows
-// c-2 .. c+2) in the ring.  Tap 5 (row c + 3) is not needed: its weight is < 1e-25 (checked on the host, `pattern`
-// in plan.cpp), so for a centre v >= 1 it adds less than 2^-80 of the running sum (no change in double), and for
-// v = 0 the quantiser returns 0 whatever the sign of the residues (full_TB.h:29-37), which is the copy.
-template <int A, int N, int D, int KM, int RING, int SWM>
-__device__ __forceinline__ int fix_phase0_bytes(const V6Params &p, uint32_t col, int slot_c, int y, uint32_t vmask, uint2 &q) {
-    static_assert(A == 3 && KM == 0x11, "written for the +-2 residues of a = 3");
-    constexpr int TAPS = 2 * A;
-    int slot0 = slot_c - 2;
-    if (slot0 < 0) slot0 += RING;
-    uint32_t hx[5][4];
+// Phase-0 second look of the V pass, once per chunk: when the hot filter flagged any phase-0 row of the chunk, ALL of
+// them are redone with the exact fp32 chain (phase0_chain2's arithmetic: the reference's double sum restated, v or
+// v - 1) and stored again.  The centres that complete in chunk rows 0 .. RB-1 use ring rows -4 .. RB-1 (a row goes
+// out when row c + 2 has arrived; the tail of the previous ring region is still there; rows before the segment's
+// first belong to output rows outside [ys, ye), which are skipped).  Every ring row is loaded once per pass and feeds
+// the sums of the up to five centres it is a tap of.
+//   * four byte-columns per pass, passes not unrolled: the caller's partial sums stay in registers across this call,
+//     so whatever this function needs beyond ~30 registers is spilled around it -- and ptxas then also spills inside
+//     the hot loop (measured: +4 % on image-like content with six converted rows of 4 columns held at once);
+//   * a byte loaded with LDS.U8 is, read as fp32, the denormal b * 2^-149, and FFMA takes denormal operands at full
+//     rate: with the constants times 2^101 the chain runs on b * 2^-24 like the hot path's values (every intermediate
+//     a normal number: the same roundings), then one exact multiplication by 2^24.
+// col: shared address of the lane's column in ring row 0; bslot: ring slot of the chunk's first row; ocol: the lane's
+// column in output row ybase (the row the period of the chunk's first iteration starts at).
+template <int A, int N, int D, int S0, int RB, int RING, int SWM>
+__device__ __noinline__ void v_fix_phase0_chunk(const V6Params &p, uint32_t col, int bslot, int ybase, uint8_t *ocol, long long opitch,
+                                                int nbytes, int ys, int ye) {
+    static_assert(A == 3, "written for the +-2 residues of a = 3");
+    float kd[5];
 #pragma unroll
-    for (int k = 0; k < 5; k++) {
-        int sl = slot0 + k;
-        if (sl >= RING) sl -= RING;
-        const uint2 w = lds_v2(col + sl * SWM);
-        hx[k][0] = __byte_perm(w.x, 0u, 0x4140); hx[k][1] = __byte_perm(w.x, 0u, 0x4342);
-        hx[k][2] = __byte_perm(w.y, 0u, 0x4140); hx[k][3] = __byte_perm(w.y, 0u, 0x4342);
-    }
-    uint32_t dz[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) dz[i] = phase0_doubt2(hx[0][i], hx[1][i], hx[2][i], hx[3][i], hx[4][i], p.p0_nk0, p.p0_k1, p.p0_k3, p.p0_nk4);
-    // sign bits (bits 15 / 31 of dz[i] = bytes 2i / 2i+1) -> bit 7 of byte e, then one bit per byte
-    const uint32_t lo = __byte_perm(dz[0], dz[1], 0x7531), hi = __byte_perm(dz[2], dz[3], 0x7531);
-    int n = 0;
+    for (int k = 0; k < 5; k++) kd[k] = p.p0c[k] * 2.535301200456459e30f;       // 2^101, exact
+    // rows -4 .. -1 are the last four of the other ring region (REGIONS = 2: bslot is 0 or RB)
+    const uint32_t a_prev = col + (bslot == 0 ? RING - 4 : bslot - 4) * SWM + 4 * SWM, a_cur = col + bslot * SWM;
+    const bool all_rows = (ybase >= ys) && (ybase + N * ((S0 + RB - 1 + A - 2) / D) < ye);
 #pragma unroll 1
-    for (uint32_t need = (sign4_to_bits(lo) | (sign4_to_bits(hi) << 4)) & vmask; need; need &= need - 1) {
-        const int e = __ffs(need) - 1;
-        const int sh = 8 * (e & 3);
-        if (((((e < 4) ? q.x : q.y) >> sh) & 0xffu) == 0u) continue;       // v = 0: clamped to 0 either way
-        uint32_t v;
-        if (p.uniform_y && N <= 8) v = exact_ring<5, RING, SWM>(col + e, slot0, [&](int k) { return p.wdtab[k]; });
-        else v = exact_ring<5, RING, SWM>(col + e, slot0, [&](int k) { return p.wdy[(long long)y * TAPS + k]; });
-        if (e < 4) q.x = (q.x & ~(0xffu << sh)) | (v << sh);
-        else q.y = (q.y & ~(0xffu << sh)) | (v << sh);
-        n++;
+    for (int half = 0; half < 2; half++) {
+        if (4 * half >= nbytes) break;
+        float2 sum[RB][2];                   // sums of the centre that completes at chunk row j (alive for five rows)
+        uint8_t *orow = ocol + 4 * half;
+        int yprev = 0;
+#pragma unroll
+        for (int jj = -4; jj < RB; jj++) {
+            bool used = false;
+#pragma unroll
+            for (int j = 0; j < RB; j++)
+                if ((S0 + j + A) % D == 0 && jj >= j - 4 && jj <= j) used = true;
+            if (!used) continue;
+            const uint32_t a = (jj < 0 ? a_prev : a_cur) + 4 * half + jj * SWM;
+            const float2 xa = make_float2(__uint_as_float(lds_u8(a)), __uint_as_float(lds_u8(a + 1)));
+            const float2 xb = make_float2(__uint_as_float(lds_u8(a + 2)), __uint_as_float(lds_u8(a + 3)));
+#pragma unroll
+            for (int j = 0; j < RB; j++) {
+                if ((S0 + j + A) % D != 0) continue;
+                const int k = jj - (j - 4);
+                if (k < 0 || k > 4) continue;
+                const float2 kk = make_float2(kd[k], kd[k]);
+                if (k == 0) { sum[j][0] = __fmul2_rn(xa, kk); sum[j][1] = __fmul2_rn(xb, kk); }
+                else { sum[j][0] = __ffma2_rn(xa, kk, sum[j][0]); sum[j][1] = __ffma2_rn(xb, kk, sum[j][1]); }
+                if (k == 4) {
+                    const int yoff = N * ((S0 + j + A - 2) / D);
+                    orow += (long long)(yoff - yprev) * opitch;
+                    yprev = yoff;
+                    const float2 u2 = make_float2(16777216.f, 16777216.f);
+                    const float2 ra = __fmul2_rn(sum[j][0], u2), rb = __fmul2_rn(sum[j][1], u2);
+                    const uint32_t q = quantise4(ra.x, ra.y, rb.x, rb.y);
+                    // predicated store, no branch: rows outside [ys, ye) (warm-up rows, rows of the next segment) are skipped
+                    const uint32_t ok = (all_rows || (ybase + yoff >= ys && ybase + yoff < ye)) ? 1u : 0u;
+                    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.u32 [%0], %1;\n\t}" ::"l"(orow), "r"(q), "r"(ok) : "memory");
+                }
+            }
+        }
     }
-    return n;
 }
 
 // col: shared address of the lane's column in ring row 0; slot_it: ring slot of the iteration's first row; yit / op:
-// output row the iteration's period starts at and the lane's column in that row; zmask: 0x80008000, or 0 with
-// LANCZOS_FLAG_FAST_ALIGNED (phase-0 rows stay copies).  Returns the number of samples evaluated in double.
-template <int A, int N, int D, int KM, int VU, int S0, int RING, int SWM, bool ST64>
+// output row the iteration's period starts at and the lane's column in that row.  Returns the number of samples
+// evaluated in double.
+template <int A, int N, int D, int VU, int S0, int RING, int SWM, bool ST64>
 __device__ __noinline__ int v_fix_iter(const V6Params &p, uint32_t col, int slot_it, int yit, uint8_t *op, long long opitch,
-                                       const VIterFlags<viter_interp_rows<A, N, D, VU, S0>(), viter_centre_rows<A, N, D, VU, S0>()> f,
-                                       uint32_t zmask, int nbytes, int ys, int ye) {
+                                       const VIterFlags<viter_interp_rows<A, N, D, VU, S0>()> f, int nbytes, int ys, int ye) {
     const uint32_t vmask = nbytes >= 8 ? 0xffu : ((1u << nbytes) - 1u);
-    int n = 0, qi = 0, zi = 0;
+    int n = 0, qi = 0;
     auto redo = [&](int yoff, auto fix) {
         const int y = yit + yoff;
         if (y < ys || y >= ye) return;                     // never stored (warm-up rows, rows of the next segment)
@@ -500,16 +520,6 @@ __device__ __noinline__ int v_fix_iter(const V6Params &p, uint32_t col, int slot
 #pragma unroll
     for (int u = 0; u < VU; u++) {
         const int s0 = (S0 + u) % D, tq = (S0 + u) / D;
-        if ((s0 + A) % D == 0) {
-            if constexpr (KM != 0) {
-                if ((f.zr[zi] & zmask) != 0u) {
-                    int slot_c = slot_it + u - 2;
-                    if (slot_c < 0) slot_c += RING;
-                    redo(N * ((S0 + u + A - 2) / D), [&](int y, uint2 &q) { return fix_phase0_bytes<A, N, D, KM, RING, SWM>(p, col, slot_c, y, vmask, q); });
-                }
-            }
-            zi++;
-        }
 #pragma unroll
         for (int yr = ylo6<N, D>(s0); yr < yhi6<N, D>(s0); yr++) {
             if ((yr * D) % N == 0) continue;
@@ -750,6 +760,50 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
                             zor |= __float_as_uint(z);
                         }
                     }
+#ifdef LZB_HCHAIN_INLINE
+                if (__builtin_expect((int)zor < 0, 0)) {
+                    float cr[PH * C];
+#pragma unroll
+                    for (int per = 0; per < PH; per++)
+#pragma unroll
+                        for (int c = 0; c < C; c += 2) {
+                            const int base = G::MIS + per * D * C + c;
+                            if (c + 1 < C) {
+                                float2 xs[5];
+#pragma unroll
+                                for (int k = 0; k < 5; k++) xs[k] = make_float2(f[base + k * C], f[base + k * C + 1]);
+                                const float2 r = phase0_chain2(xs, p.p0c);
+                                cr[per * C + c] = r.x;
+                                cr[per * C + c + 1] = r.y;
+                            } else {
+                                float xs[5];
+#pragma unroll
+                                for (int k = 0; k < 5; k++) xs[k] = f[base + k * C];
+                                cr[per * C + c] = phase0_chain1(xs, p.p0c);
+                            }
+                        }
+#pragma unroll
+                    for (int wi = 0; wi < 2 * G::NW2; wi++) {
+                        float rr[4] = {0.f, 0.f, 0.f, 0.f};
+                        uint32_t sel = 0x3210u;
+                        bool any = false;
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const int j = 4 * wi + e - G::MIS - CEN * C;      // input byte of the item, 0 = its first own byte
+                            if (j >= 0 && j < PH * D * C && (j / C) % D == 0) {
+                                rr[e] = cr[((j / C) / D) * C + j % C];
+                                sel = (sel & ~(0xfu << (4 * e))) | ((uint32_t)(4 + e) << (4 * e));
+                                any = true;
+                            }
+                        }
+                        if (any) {
+                            const uint32_t q = quantise4(rr[0], rr[1], rr[2], rr[3]);
+                            srcw[wi] = (sel == 0x7654u) ? q : __byte_perm(srcw[wi], q, sel);
+                        }
+                    }
+                    zor = 0;
+                }
+#endif
             }
 #endif
             // splice copies (raw input bytes) and interpolated bytes into the output words
@@ -788,7 +842,7 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
                 a.in_row = &sm.in[st][lr * G::BOX_B + xshift]; a.ring_row = drow; a.gbyte0 = g * G::OUT_B;
                 a.obyte0 = obyte0; a.ibyte0 = ibyte0; a.valid_bytes = hvalid;
                 a.fix_g = fix_g; a.fix_z = zor >> 31; a.guard = guard_h;
-                n_strict += h_fix<C, A, N, D, PH, KM, G::PAD_L>(p, a);
+                n_strict += h_fix<G, C, A, N, D, PH, KM>(p, a);
             }
         }
     };
@@ -825,7 +879,7 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
     int ybase = N * t0_first;                                  // output row that period t of the chunk's first iteration starts at
     uint8_t *ocol = out_frame + vbyte0 + VB * tid + (long long)(ybase - p.out_row0) * opitch;   // column in row ybase
 
-    constexpr int NI_IT = viter_interp_rows<A, N, D, VU, G::S0>(), NZ_IT = viter_centre_rows<A, N, D, VU, G::S0>();
+    constexpr int NI_IT = viter_interp_rows<A, N, D, VU, G::S0>();
     const uint32_t zmask = p.strict_v_identity ? 0x80008000u : 0u;   // LANCZOS_FLAG_FAST_ALIGNED: phase-0 rows stay plain copies
 
     auto v_pass = [&](int chunk) {
@@ -833,6 +887,7 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
         const uint8_t *vrow = vcol + bslot * SWM;
         // rows [ybase, ybase + YROWS + N * (A + 2) / D] can be stored by this chunk
         const bool interior = (ybase - N >= ys) && (ybase + G::YROWS + N * (A + 2) <= ye);
+        uint32_t zchunk = 0;                                   // sign bits: some phase-0 row of the chunk may flip (FILTER)
         auto body = [&](auto check_tag) {
             constexpr bool CHECK = decltype(check_tag)::value;
             const uint8_t *vit = vrow;                         // first row of the iteration
@@ -840,8 +895,8 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
             int yit = ybase;
 #pragma unroll 1
             for (int it = 0; it < G::RB / VU; it++) {
-                VIterFlags<NI_IT, NZ_IT> fl;                   // what says "look again" (MODE 0), see v_fix_iter
-                int qi = 0, zi = 0;
+                VIterFlags<NI_IT> fl;                          // what says "look again" (MODE 0), see v_fix_iter
+                int qi = 0;
 #pragma unroll
                 for (int u = 0; u < VU; u++) {
                     const int s0 = (G::S0 + u) % D, tq = (G::S0 + u) / D;   // completing centre = D*(t + tq) + s0
@@ -931,13 +986,13 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
                                 zpre |= hfma2_u(zA[zs][i], kR, hn[i]);
                                 zA[zs][i] = hn[i];
                             }
-                            fl.zr[zi] = zpost;
+                            // (rows outside [ys, ye) -- warm-up rows, rows of the next segment -- are never stored: no second look)
+                            if (!CHECK || (yit + N * ((G::S0 + u + A - 2) / D) >= ys && yit + N * ((G::S0 + u + A - 2) / D) < ye)) zchunk |= zpost;
                             zP[zs] = zpre;
                         } else {
                             qv = wP[zs];
                             wP[zs] = w;
                         }
-                        zi++;
                         store_row(N * ((G::S0 + u + A - 2) / D), qv);
                     }
                     // ---- interpolated rows that received their last tap ----
@@ -972,15 +1027,9 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
                     uint32_t any = 0;
 #pragma unroll
                     for (int j = 0; j < NI_IT; j++) any |= fl.dx[j] | fl.dy[j];
-                    if (FILTER) {
-                        uint32_t anyz = 0;
-#pragma unroll
-                        for (int j = 0; j < NZ_IT; j++) anyz |= fl.zr[j];
-                        any |= anyz & zmask;
-                    }
                     if (any != 0u)
-                        n_strict += v_fix_iter<A, N, D, FILTER ? KM : 0, VU, G::S0, G::RING, SWM, ST64>(
-                            p, vcol_s, (int)((uint32_t)(vit - vcol) / (uint32_t)SWM), yit, op, opitch, fl, zmask, valid_bytes - VB * tid, ys, ye);
+                        n_strict += v_fix_iter<A, N, D, VU, G::S0, G::RING, SWM, ST64>(
+                            p, vcol_s, (int)((uint32_t)(vit - vcol) / (uint32_t)SWM), yit, op, opitch, fl, valid_bytes - VB * tid, ys, ye);
                 }
                 vit += VU * SWM;
                 yit += N * VU / D;
@@ -988,6 +1037,11 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
             }
         };
         if (interior) body(std::false_type{}); else body(std::true_type{});
+        // rare: the reference may return v - 1 somewhere in the phase-0 rows of this chunk -> all of them again, exactly
+        if constexpr (FILTER) {
+            if ((zchunk & zmask) != 0u)
+                v_fix_phase0_chunk<A, N, D, G::S0, G::RB, G::RING, SWM>(p, vcol_s, bslot, ybase, ocol, opitch, valid_bytes - VB * tid, ys, ye);
+        }
         ybase += G::YROWS;
         ocol += (long long)G::YROWS * opitch;
     };
@@ -1110,8 +1164,7 @@ int launch_v6_one(const KParams &k, const FastHostTables &t, int *alias_in_kerne
         *alias_in_kernel = 1;
     }
     for (int i = 0; i < 8; i++) p.align_k[i] = i < 2 * A ? t.align_k[i] : 0.f;
-    for (int i = 0; i < 8; i++) p.align_ki[i] = (int)std::ceil((double)p.align_k[i] * 65536.0 * 1.0001);
-    p.p0_nk0 = t.p0_half2[0]; p.p0_k1 = t.p0_half2[1]; p.p0_k3 = t.p0_half2[2]; p.p0_nk4 = t.p0_half2[3];
+    for (int i = 0; i < 5; i++) p.p0c[i] = t.p0_chain ? t.p0_chain[i] * 16777216.f : 0.f;   // x 2^24, exact
     for (int ph = 0; ph < N; ph++)
         for (int q = 0; q < 8; q++) p.wtab[ph * 8 + q] = q < 2 * A ? t.phase_w[ph * 2 * A + q] * 16777216.f : 0.f;  // x 2^24, see kPixUnscale
     for (int ph = 0; ph < N && ph < 8; ph++)
@@ -1166,8 +1219,8 @@ int launch_v6(const KParams &k, const FastHostTables &t, int *kernel_id, int *al
         return st64 ? launch_v6_one<c, a, n, d, ph, kmask, LZB_W, 1, true>(k, t, alias_in_kernel, s)                        \
                     : launch_v6_one<c, a, n, d, ph, kmask, LZB_W, 1, false>(k, t, alias_in_kernel, s);                      \
     }
-    // the phase-0 rows are decided with taps 0..4 only (v_fix_phase0): needs the residue pattern plan.cpp checks
-    if (km != 0 && t.p0_half2[0] == 0xFC00FC00u) return -1;
+    // the phase-0 second look is the exact fp32 chain (phase0_chain2): only with plan.cpp's proof for these weights
+    if (km != 0 && !t.p0_chain) return -1;
     // a = 3: sin(2*pi) < 0 in double, so the |d| = 2 taps (k = 0 and k = 4) carry negative residues
     LZ6_CASE(3, 3, 2, 1, 8, 0x11, 1)
 #ifndef LZB_V6_DEV   // development builds (tools/build_variant.sh -DLZB_V6_DEV): the headline instance only

@@ -7,6 +7,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
+#include <mutex>
 #include <numeric>
 
 #ifndef M_PI
@@ -24,21 +26,82 @@ static double sinc_ref(double x) {
 // full_TB.h:51-53 (LANCZOS_A is an int macro: M_PI*x/a divides by (double)a)
 double ref_kernel(double x, int a) { return sinc_ref(M_PI * x) * sinc_ref(M_PI * x / a); }
 
-uint32_t half2_bits(double x, bool away) {
-    const double ax = std::fabs(x);
-    uint32_t h = 0;
-    if (ax >= 65504.0) h = away ? 0x7C00u : 0x7BFFu;
-    else if (ax > 0) {
-        int e;
-        std::frexp(ax, &e);                    // ax = m * 2^e, m in [0.5, 1)
-        const int ex = std::max(e - 1, -14);   // fp16 exponent (subnormals share -14)
-        const double q = std::ldexp(ax, 10 - ex);              // in units of the fp16 spacing at this exponent
-        const double m = away ? std::ceil(q) : std::floor(q);
-        // normals: (ex + 15) << 10 | (m - 1024), a carry into the exponent included; subnormals: m itself
-        h = (ax >= std::ldexp(1.0, -14)) ? (uint32_t)(((ex + 15) << 10) + ((int)m - 1024)) : (uint32_t)m;
-    }
-    if (x < 0) h |= 0x8000u;
-    return h | (h << 16);
+// Phase-0 sum of the reference in fp32 (lanczos_v6.cu phase0 chain; tools/phase0_affine_proof.py is the same proof
+// in numpy).  The reference adds, in double and in this order, b0*w0, b1*w1, v*1, b3*w3, b4*w4 (tap 5 is < 1e-25 and
+// never changes the sum): residues of ~1e-15 against a centre v whose neighbouring doubles are u = 2^(e-52) apart
+// (v in [2^e, 2^(e+1)); u/2 below a power of two).  What comes out, v or v - 1, is decided by how the residues round
+// on that grid.  The fp32 grid around the same v is the double grid scaled by exactly 2^29 in every binade (24
+// against 53 significand bits; the halving below powers of two and the parity of the last bit included, v being an
+// integer < 256), so the same sum with residues scaled by 2^29 makes the same decisions -- unless an fp32 rounding
+// error of the scaled residues (W_k carries 24 bits) moves a value across a rounding boundary.  That cannot be argued
+// away, but it can be enumerated: the sum after the centre tap is v + k*u/2 with a few dozen possible k, so
+//   stage 1: every (v, b0, b1)            -> k2 (16.7 M cases)
+//   stage 2: every (v, reachable k2, b3)  -> k3
+//   stage 3: every (v, reachable k3, b4)  -> k4 and the truncated result
+// are compared between the two arithmetics, each stage starting from the exact common state.
+bool verify_phase0_chain(const double *w, float *W) {
+    if (!(w[0] < 0 && w[4] < 0 && w[1] > 0 && w[3] > 0 && w[2] == 1.0 && std::fabs(w[5]) < 1e-25)) return false;
+    const double S29 = std::ldexp(1.0, 29);
+    W[0] = (float)(w[0] * S29); W[1] = (float)(w[1] * S29); W[2] = 1.f; W[3] = (float)(w[3] * S29); W[4] = (float)(w[4] * S29);
+    // the same for every plan with these weights: verified once per process
+    static std::mutex mu;
+    static double seen_w[6];
+    static int seen = -1;
+    std::lock_guard<std::mutex> lock(mu);
+    if (seen >= 0 && std::memcmp(seen_w, w, sizeof seen_w) == 0) return seen == 1;
+    auto run = [&]() -> bool {
+        std::vector<double> s1(65536);
+        std::vector<float> y1(65536);
+        for (int b0 = 0; b0 < 256; b0++)
+            for (int b1 = 0; b1 < 256; b1++) {
+                const double p0 = (double)b0 * w[0], p1 = (double)b1 * w[1];
+                s1[b0 * 256 + b1] = p0 + p1;
+                const float t = (float)b0 * W[0];
+                y1[b0 * 256 + b1] = std::fmaf((float)b1, W[1], t);
+            }
+        constexpr int KR = 512;                       // states are k in (-KR, KR) half-spacings
+        for (int v = 1; v < 256; v++) {
+            int e = 0;
+            while ((2 << e) <= v) e++;
+            const double hs = std::ldexp(1.0, e - 53), HS = hs * S29;
+            const double dv = (double)v;
+            const float fv = (float)v;
+            bool st2[2 * KR] = {}, st3[2 * KR] = {}, st4[2 * KR] = {};
+            auto same = [&](double s, float X, bool *mark) {
+                const double k64 = (s - dv) / hs, k32 = ((double)X - dv) / HS;
+                if (k64 != k32 || k64 != std::rint(k64) || std::fabs(k64) >= KR) return false;
+                mark[(int)k64 + KR] = true;
+                return true;
+            };
+            for (int i = 0; i < 65536; i++) {
+                const double s2 = s1[i] + dv * w[2];
+                const float X2 = fv + y1[i];
+                if (!same(s2, X2, st2)) return false;
+            }
+            for (int stage = 0; stage < 2; stage++) {
+                const bool *from = stage ? st3 : st2;
+                bool *to = stage ? st4 : st3;
+                const int tap = stage ? 4 : 3;
+                for (int k = -KR + 1; k < KR; k++) {
+                    if (!from[k + KR]) continue;
+                    const double s_in = dv + k * hs;
+                    const float X_in = (float)(dv + k * HS);
+                    if ((double)X_in != dv + k * HS || (s_in - dv) / hs != (double)k) return false;   // the common state is exact in both
+                    for (int b = 0; b < 256; b++) {
+                        const double s = s_in + (double)b * w[tap];
+                        const float X = std::fmaf((float)b, W[tap], X_in);
+                        if (!same(s, X, to)) return false;
+                        if (stage == 1 && std::trunc(s) != (double)std::trunc(X)) return false;
+                    }
+                }
+            }
+        }
+        return true;
+    };
+    const bool ok = run();
+    std::memcpy(seen_w, w, sizeof seen_w);
+    seen = ok ? 1 : 0;
+    return ok;
 }
 
 int resolve_desc(const lanczos_desc *in, lanczos_desc *out) {
@@ -175,24 +238,10 @@ int build_plan(const lanczos_desc *desc, Plan *out) {
             if (K > 1e-7) p.align_k[k] = (float)(K * (1.0 + 1e-6));
         }
     }
-    // Sharper phase-0 test of the slow paths (lanczos_v6.cu phase0_doubt2), a = 3: with H = 2^ceil(log2 v) and
-    // K_k = |w_k| * 2^54 the reference returns v if  K0 b0 - K1 b1 <= H  and  (K4 b4 <= H  or  K3 b3 - K4 b4 >= 2H).
-    // Negative residues get the 1/0.99 margin (rounding of the reference's own products) and are rounded away
-    // from zero; positive ones get 0.99 * (1 - 2^-10) (the second factor covers the rounding of the first of
-    // two chained fp16 FMAs) and are rounded toward zero.  A residue with the wrong sign disables its term.
-    if (a == 3) {
-        const double *w0 = p.phase_wd.data();       // phase 0
-        const double S = std::ldexp(1.0, 54 + 12);  // the kernel's fp16 values carry 2^-12
-        auto neg_k = [&](double w) { return half2_bits(w * S / 0.99, true); };
-        auto pos_k = [&](double w) { return half2_bits(w * S * 0.99 * (1.0 - 1.0 / 1024.0), false); };
-        // the argument holds for this sign pattern only (taps 0 and 4 pull down, 1 and 3 lift, tap 5 is far
-        // below half an ulp of 1); anything else: every sample stays in doubt (-inf constants)
-        const bool pattern = w0[0] < 0 && w0[4] < 0 && w0[1] > 0 && w0[3] > 0 && w0[2] == 1.0 && std::fabs(w0[5]) < 1e-25;
-        p.p0_half2[0] = pattern ? neg_k(w0[0]) : 0xFC00FC00u;
-        p.p0_half2[1] = pattern ? pos_k(w0[1]) : 0u;
-        p.p0_half2[2] = pattern ? pos_k(w0[3]) : 0u;
-        p.p0_half2[3] = pattern ? neg_k(w0[4]) : 0xFC00FC00u;
-    }
+    // Phase-0 second look of lanczos_v6.cu (a = 3): the reference's sum restated exactly in fp32, see verify_phase0_chain.
+    // It holds for the sign pattern of a = 3 only (taps 0 and 4 pull down, 1 and 3 lift, tap 5 is far below half an
+    // ulp of 1) and is proved by enumeration for the very weights of this plan.
+    if (a == 3) p.p0_chain_ok = verify_phase0_chain(p.phase_wd.data(), p.p0_chain);
     rc = build_axis(p.x, p.d.out_w, p.d.in_w, a, n, dd, p.phase_w, p.phase_wd);
     if (rc != LANCZOS_OK) return rc;
     rc = build_axis(p.y, p.d.out_h, p.d.in_h, a, n, dd, p.phase_w, p.phase_wd);

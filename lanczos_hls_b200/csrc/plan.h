@@ -38,9 +38,11 @@ struct Plan {
     float guard = 0;             // |sum - nearest integer| below this -> exact re-evaluation
     float guard_asc = 0, guard_outer = 0;   // tighter guards of the second-generation kernels (see AxisTables)
     std::vector<float> align_k;  // [2a] phase-0 "cannot flip" filter constants (see plan.cpp)
-    // a = 3 only: fp16x2 constants (both lanes equal, times 2^12) of the sharper phase-0 re-check used by the
-    // slow paths of lanczos_v6.cu (phase0_doubt2): {-K0, +K1, +K3, -K4}, K_k = |w_k| * 2^54 (see plan.cpp)
-    uint32_t p0_half2[4] = {0, 0, 0, 0};
+    // a = 3, phase-0 coordinates exactly integral: the reference's double sum restated EXACTLY in fp32 (plan.cpp
+    // verify_phase0_chain): {W0, W1, 1, W3, W4} with W_k = fl32(w_k * 2^29).  p0_chain_ok = the enumeration over every
+    // reachable state of the sum found no difference; kernels that rely on the chain are not used without it.
+    float p0_chain[5] = {0, 0, 0, 0, 0};
+    bool p0_chain_ok = false;
     // in-place aliasing (full_TB.h:67-77): rows [0,alias_rows) read already-final rows
     int alias_rows = 0;     // K0
     int alias_top_row = -1; // M: largest row read by an aliased row (-1 if none)
@@ -53,8 +55,10 @@ int resolve_desc(const lanczos_desc *in, lanczos_desc *out);
 // Build all host tables. `out` must outlive device uploads.
 int build_plan(const lanczos_desc *desc, Plan *out);
 
-// fp16x2 word with both lanes = x rounded to fp16 away from zero (`away`) or toward zero.
-uint32_t half2_bits(double x, bool away);
+// The phase-0 sum of the reference (a = 3; w = its six double weights at integer distances) against its fp32
+// restatement t = b0*W0, y = fma(b1, W1, t), X2 = v + y, X3 = fma(b3, W3, X2), X4 = fma(b4, W4, X3): true when
+// trunc(X4) equals the reference's result for EVERY (b0, b1, v, b3, b4), by enumeration of the states of the sum.
+bool verify_phase0_chain(const double *w, float *W);
 
 // The reference kernel, full_TB.h:39-53.
 double ref_kernel(double x, int a);
