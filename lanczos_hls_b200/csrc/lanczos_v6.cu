@@ -23,9 +23,13 @@
 //      destination does the window shift, so the loop body is one ratio period and the code stays small enough
 //      for the instruction cache); the row that received its last tap is quantised and stored (STG.64).
 //      The phase-0 "cannot flip" test runs on the fp16x2 pipe with exact small-integer arithmetic
-//      (8*v - 3*(b[-2]+b[+2]) >= 0, a conservative form of plan.cpp's filter).
+//      (8*v - 3*b[+-2] >= 0 per side, a conservative form of plan.cpp's filter).
 // Exactness: sums start at -guard; a sample whose truncation differs between x-guard and x+guard is
 // recomputed with the reference's double arithmetic (full_TB.h:58-63) by the thread that found it.
+// Phase-0 samples (output coordinate on an input sample: the reference returns the centre value v or v - 1) are
+// copies of v where the cheap filter proves that, and are otherwise decided by an EXACT fp32 restatement of the
+// reference's double sum (phase0_chain2; proved by enumeration in plan.cpp verify_phase0_chain): in line in the H
+// pass (the converted bytes are in registers), once per chunk and out of line in the V pass (v_fix_phase0_chunk).
 // MODE 1 (LANCZOS_FLAG_TOLERANCE_1LSB): the V pass is plain fp32 (no guard, no phase-0 test); the H pass
 // stays exact, so every output byte is within 1 LSB of the reference.
 #include <algorithm>
@@ -238,17 +242,6 @@ __device__ __forceinline__ float2 phase0_chain2(const float2 (&x)[5], const floa
     for (int k = 1; k < 5; k++) s = __ffma2_rn(x[k], make_float2(pc[k], pc[k]), s);
     return s;
 }
-// fp32 multiply / FMA WITHOUT .ftz whatever the compilation flags say (a denormal operand must not be flushed)
-__device__ __forceinline__ float fmul_keep_denormals(float a, float b) {
-    float d;
-    asm("mul.rn.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
-    return d;
-}
-__device__ __forceinline__ float fma_keep_denormals(float a, float b, float c) {
-    float d;
-    asm("fma.rn.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
-    return d;
-}
 __device__ __forceinline__ float phase0_chain1(const float (&x)[5], const float *pc) {
     float s = __fmul_rn(x[0], pc[0]);
 #pragma unroll
@@ -274,68 +267,15 @@ struct HFixArgs {
     int gbyte0;               // strip-relative output byte of the item's first byte
     int obyte0, ibyte0, valid_bytes;
     uint32_t fix_g;           // bit per packed word of interpolated samples
-    uint32_t fix_z;           // some phase-0 sample of the item may flip
     float guard;
 };
 
-template <class G, int C, int A, int N, int D, int PH, int KM>
+template <class G, int C, int A, int N, int D, int PH>
 __device__ __noinline__ int h_fix(const V6Params &p, const HFixArgs a) {
     constexpr int TAPS = 2 * A;
     constexpr int NI = PH * (N - 1) * C;
     constexpr int PAD_L = G::PAD_L;
     int n_strict = 0;
-    if constexpr (KM != 0) {
-        if (a.fix_z) {
-            // All phase-0 samples of the item again with the exact fp32 chain (phase0_chain2: the reference's double
-            // sum restated, v or v - 1): the item's window as the hot path reads it, the results spliced over the
-            // copies in the ring row.
-            static_assert(A == 3, "written for the +-2 residues of a = 3");
-            // Register-light (this function is called with the V pass's partial sums live in the caller, see
-            // v_fix_phase0_chunk): the window bytes are taken one after the other, each feeding the sums of the up to
-            // five samples it is a tap of, so only the sums of ~4C + 1 samples are alive at any time.  A byte loaded with
-            // LDS.U8 is, read as fp32, the denormal b * 2^-149, and FFMA takes denormal operands at full rate: with the
-            // constants times 2^101 the chain runs on b * 2^-24 like the hot path's values do (every intermediate a
-            // normal number, so the same roundings), then one exact multiplication by 2^24.
-            const uint32_t t0 = smem_u32(a.in_row) + G::WIN0 + (a.gbyte0 / G::OUT_B) * G::IN_B + G::MIS;    // tap 0 of sample (0, 0)
-            const uint32_t dst = smem_u32(a.ring_row);
-            float kd[5];
-#pragma unroll
-            for (int k = 0; k < 5; k++) kd[k] = p.p0c[k] * 2.535301200456459e30f;       // 2^101, exact
-            constexpr int NBYTES = (PH - 1) * D * C + C + 4 * C;       // window bytes the phase-0 samples of the item touch
-            float sum[PH * C];
-            float fin[4];
-            int fpos[4];
-            int nfin = 0;
-#pragma unroll
-            for (int i = 0; i < NBYTES; i++) {
-                const float x = __uint_as_float(lds_u8(t0 + i));
-#pragma unroll
-                for (int k = 0; k < 5; k++) {
-                    const int sb = i - k * C;                              // tap-0 byte of the sample this byte is tap k of
-                    if (sb < 0 || (sb / C) % D != 0 || (sb / C) / D >= PH) continue;
-                    const int sidx = ((sb / C) / D) * C + sb % C;
-                    if (k == 0) sum[sidx] = fmul_keep_denormals(x, kd[0]);
-                    else sum[sidx] = fma_keep_denormals(x, kd[k], sum[sidx]);
-                    if (k == 4) {
-                        fin[nfin] = sum[sidx] * 16777216.f;
-                        fpos[nfin] = ((sb / C) / D) * N * C + sb % C;    // output byte of the sample inside the item
-                        nfin++;
-                    }
-                }
-                if (nfin == 4 || (i == NBYTES - 1 && nfin > 0)) {
-                    const uint32_t q = quantise4(fin[0], nfin > 1 ? fin[1] : 0.f, nfin > 2 ? fin[2] : 0.f, nfin > 3 ? fin[3] : 0.f);
-                    if (nfin == 4 && fpos[0] % 4 == 0 && fpos[1] == fpos[0] + 1 && fpos[2] == fpos[0] + 2 && fpos[3] == fpos[0] + 3) {
-                        asm volatile("st.shared.u32 [%0], %1;" ::"r"(dst + fpos[0]), "r"(q) : "memory");
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 4; e++)
-                            if (e < nfin) asm volatile("st.shared.u8 [%0], %1;" ::"r"(dst + fpos[e]), "r"(q >> (8 * e)) : "memory");
-                    }
-                    nfin = 0;
-                }
-            }
-        }
-    }
     auto fix_byte = [&](int b) {
         if (a.gbyte0 + b >= a.valid_bytes) return;
         const int ob = a.obyte0 + a.gbyte0 + b;                  // global output byte column
@@ -695,6 +635,72 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
                 word_to_f32x4(w.x, f[8 * wi], f[8 * wi + 1], f[8 * wi + 2], f[8 * wi + 3]);
                 word_to_f32x4(w.y, f[8 * wi + 4], f[8 * wi + 5], f[8 * wi + 6], f[8 * wi + 7]);
             }
+            // phase-0 samples are copies of the centre tap; "cannot flip" filter of plan.cpp:
+            // v - sum K_k*b_k >= 0 over the negative residues -> the reference returns v as well
+#ifndef LZB_ABL_NOHFILTER
+            if (KM != 0) {
+#pragma unroll
+                for (int per = 0; per < PH; per++)
+#pragma unroll
+                    for (int c = 0; c < C; c += 2) {
+                        const int base = G::MIS + per * D * C + c;
+                        if (c + 1 < C) {
+                            float2 z = make_float2(f[base + CEN * C], f[base + CEN * C + 1]);
+#pragma unroll
+                            for (int k = 0; k < TAPS; k++)
+                                if ((KM >> k) & 1) z = __ffma2_rn(make_float2(f[base + k * C], f[base + k * C + 1]), make_float2(-p.align_k[k], -p.align_k[k]), z);
+                            zor |= __float_as_uint(z.x) | __float_as_uint(z.y);
+                        } else {
+                            float z = f[base + CEN * C];
+#pragma unroll
+                            for (int k = 0; k < TAPS; k++)
+                                if ((KM >> k) & 1) z = fmaf(f[base + k * C], -p.align_k[k], z);
+                            zor |= __float_as_uint(z);
+                        }
+                    }
+                if ((int)zor < 0) {
+                    float cr[PH * C];
+#pragma unroll
+                    for (int per = 0; per < PH; per++)
+#pragma unroll
+                        for (int c = 0; c < C; c += 2) {
+                            const int base = G::MIS + per * D * C + c;
+                            if (c + 1 < C) {
+                                float2 xs[5];
+#pragma unroll
+                                for (int k = 0; k < 5; k++) xs[k] = make_float2(f[base + k * C], f[base + k * C + 1]);
+                                const float2 r = phase0_chain2(xs, p.p0c);
+                                cr[per * C + c] = r.x;
+                                cr[per * C + c + 1] = r.y;
+                            } else {
+                                float xs[5];
+#pragma unroll
+                                for (int k = 0; k < 5; k++) xs[k] = f[base + k * C];
+                                cr[per * C + c] = phase0_chain1(xs, p.p0c);
+                            }
+                        }
+#pragma unroll
+                    for (int wi = 0; wi < 2 * G::NW2; wi++) {
+                        float rr[4] = {0.f, 0.f, 0.f, 0.f};
+                        uint32_t sel = 0x3210u;
+                        bool any = false;
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const int j = 4 * wi + e - G::MIS - CEN * C;      // input byte of the item, 0 = its first own byte
+                            if (j >= 0 && j < PH * D * C && (j / C) % D == 0) {
+                                rr[e] = cr[((j / C) / D) * C + j % C];
+                                sel = (sel & ~(0xfu << (4 * e))) | ((uint32_t)(4 + e) << (4 * e));
+                                any = true;
+                            }
+                        }
+                        if (any) {
+                            const uint32_t q = quantise4(rr[0], rr[1], rr[2], rr[3]);
+                            srcw[wi] = (sel == 0x7654u) ? q : __byte_perm(srcw[wi], q, sel);
+                        }
+                    }
+                }
+            }
+#endif
             // window byte k (k = 0 is HALO_L bytes left of the item's own input) = f[MIS + k] * 2^24
             // interpolated samples in output order (sample s: period s / ((N-1)*C), then phase, then channel).
             // Channels c and c + 1 (c even) of a pixel use the same weights and their window bytes are neighbours:
@@ -737,75 +743,6 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
                 srcw[2 * G::NW2 + dw] = qa;
                 if (qa != qb) fix_g |= 1u << dw;
             }
-            // phase-0 samples are copies of the centre tap; "cannot flip" filter of plan.cpp:
-            // v - sum K_k*b_k >= 0 over the negative residues -> the reference returns v as well
-#ifndef LZB_ABL_NOHFILTER
-            if (KM != 0) {
-#pragma unroll
-                for (int per = 0; per < PH; per++)
-#pragma unroll
-                    for (int c = 0; c < C; c += 2) {
-                        const int base = G::MIS + per * D * C + c;
-                        if (c + 1 < C) {
-                            float2 z = make_float2(f[base + CEN * C], f[base + CEN * C + 1]);
-#pragma unroll
-                            for (int k = 0; k < TAPS; k++)
-                                if ((KM >> k) & 1) z = __ffma2_rn(make_float2(f[base + k * C], f[base + k * C + 1]), make_float2(-p.align_k[k], -p.align_k[k]), z);
-                            zor |= __float_as_uint(z.x) | __float_as_uint(z.y);
-                        } else {
-                            float z = f[base + CEN * C];
-#pragma unroll
-                            for (int k = 0; k < TAPS; k++)
-                                if ((KM >> k) & 1) z = fmaf(f[base + k * C], -p.align_k[k], z);
-                            zor |= __float_as_uint(z);
-                        }
-                    }
-#ifdef LZB_HCHAIN_INLINE
-                if (__builtin_expect((int)zor < 0, 0)) {
-                    float cr[PH * C];
-#pragma unroll
-                    for (int per = 0; per < PH; per++)
-#pragma unroll
-                        for (int c = 0; c < C; c += 2) {
-                            const int base = G::MIS + per * D * C + c;
-                            if (c + 1 < C) {
-                                float2 xs[5];
-#pragma unroll
-                                for (int k = 0; k < 5; k++) xs[k] = make_float2(f[base + k * C], f[base + k * C + 1]);
-                                const float2 r = phase0_chain2(xs, p.p0c);
-                                cr[per * C + c] = r.x;
-                                cr[per * C + c + 1] = r.y;
-                            } else {
-                                float xs[5];
-#pragma unroll
-                                for (int k = 0; k < 5; k++) xs[k] = f[base + k * C];
-                                cr[per * C + c] = phase0_chain1(xs, p.p0c);
-                            }
-                        }
-#pragma unroll
-                    for (int wi = 0; wi < 2 * G::NW2; wi++) {
-                        float rr[4] = {0.f, 0.f, 0.f, 0.f};
-                        uint32_t sel = 0x3210u;
-                        bool any = false;
-#pragma unroll
-                        for (int e = 0; e < 4; e++) {
-                            const int j = 4 * wi + e - G::MIS - CEN * C;      // input byte of the item, 0 = its first own byte
-                            if (j >= 0 && j < PH * D * C && (j / C) % D == 0) {
-                                rr[e] = cr[((j / C) / D) * C + j % C];
-                                sel = (sel & ~(0xfu << (4 * e))) | ((uint32_t)(4 + e) << (4 * e));
-                                any = true;
-                            }
-                        }
-                        if (any) {
-                            const uint32_t q = quantise4(rr[0], rr[1], rr[2], rr[3]);
-                            srcw[wi] = (sel == 0x7654u) ? q : __byte_perm(srcw[wi], q, sel);
-                        }
-                    }
-                    zor = 0;
-                }
-#endif
-            }
-#endif
             // splice copies (raw input bytes) and interpolated bytes into the output words
             uint8_t *drow = &sm.ring[slot0][dst_off];
             uint4 *dst = reinterpret_cast<uint4 *>(drow);
@@ -835,14 +772,14 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
                 }
                 dst[v4] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
             }
-            // rare: a truncation in doubt or a phase-0 sample that may flip -> this thread looks again
-            if (fix_g != 0 || (int)zor < 0) {
+            // rare: a truncation in doubt -> this thread looks again
+            if (fix_g != 0) {
                 HFixArgs a;
                 const int lr = item / groups, g = item - lr * groups;
                 a.in_row = &sm.in[st][lr * G::BOX_B + xshift]; a.ring_row = drow; a.gbyte0 = g * G::OUT_B;
                 a.obyte0 = obyte0; a.ibyte0 = ibyte0; a.valid_bytes = hvalid;
-                a.fix_g = fix_g; a.fix_z = zor >> 31; a.guard = guard_h;
-                n_strict += h_fix<G, C, A, N, D, PH, KM>(p, a);
+                a.fix_g = fix_g; a.guard = guard_h;
+                n_strict += h_fix<G, C, A, N, D, PH>(p, a);
             }
         }
     };
