@@ -397,45 +397,47 @@ __device__ __noinline__ void v_fix_phase0_chunk(const V6Params &p, uint32_t col,
     for (int k = 0; k < 5; k++) kd[k] = p.p0c[k] * 2.535301200456459e30f;       // 2^101, exact
     // rows -4 .. -1 are the last four of the other ring region (REGIONS = 2: bslot is 0 or RB)
     const uint32_t a_prev = col + (bslot == 0 ? RING - 4 : bslot - 4) * SWM + 4 * SWM, a_cur = col + bslot * SWM;
-    const bool all_rows = (ybase >= ys) && (ybase + N * ((S0 + RB - 1 + A - 2) / D) < ye);
+    auto pass = [&](auto all_tag) {
+        constexpr bool ALL = decltype(all_tag)::value;      // every row of the chunk lies inside [ys, ye): no row tests
 #pragma unroll 1
-    for (int half = 0; half < 2; half++) {
-        if (4 * half >= nbytes) break;
-        float2 sum[RB][2];                   // sums of the centre that completes at chunk row j (alive for five rows)
-        uint8_t *orow = ocol + 4 * half;
-        int yprev = 0;
+        for (int half = 0; half < 2; half++) {
+            if (4 * half >= nbytes) break;
+            float2 sum[RB][2];                   // sums of the centre that completes at chunk row j (alive for five rows)
+            uint8_t *orow = ocol + 4 * half;
+            int yprev = 0;
 #pragma unroll
-        for (int jj = -4; jj < RB; jj++) {
-            bool used = false;
+            for (int jj = -4; jj < RB; jj++) {
+                bool used = false;
 #pragma unroll
-            for (int j = 0; j < RB; j++)
-                if ((S0 + j + A) % D == 0 && jj >= j - 4 && jj <= j) used = true;
-            if (!used) continue;
-            const uint32_t a = (jj < 0 ? a_prev : a_cur) + 4 * half + jj * SWM;
-            const float2 xa = make_float2(__uint_as_float(lds_u8(a)), __uint_as_float(lds_u8(a + 1)));
-            const float2 xb = make_float2(__uint_as_float(lds_u8(a + 2)), __uint_as_float(lds_u8(a + 3)));
+                for (int j = 0; j < RB; j++)
+                    if ((S0 + j + A) % D == 0 && jj >= j - 4 && jj <= j) used = true;
+                if (!used) continue;
+                const uint32_t a = (jj < 0 ? a_prev : a_cur) + 4 * half + jj * SWM;
+                const float2 xa = make_float2(__uint_as_float(lds_u8(a)), __uint_as_float(lds_u8(a + 1)));
+                const float2 xb = make_float2(__uint_as_float(lds_u8(a + 2)), __uint_as_float(lds_u8(a + 3)));
 #pragma unroll
-            for (int j = 0; j < RB; j++) {
-                if ((S0 + j + A) % D != 0) continue;
-                const int k = jj - (j - 4);
-                if (k < 0 || k > 4) continue;
-                const float2 kk = make_float2(kd[k], kd[k]);
-                if (k == 0) { sum[j][0] = __fmul2_rn(xa, kk); sum[j][1] = __fmul2_rn(xb, kk); }
-                else { sum[j][0] = __ffma2_rn(xa, kk, sum[j][0]); sum[j][1] = __ffma2_rn(xb, kk, sum[j][1]); }
-                if (k == 4) {
-                    const int yoff = N * ((S0 + j + A - 2) / D);
-                    orow += (long long)(yoff - yprev) * opitch;
-                    yprev = yoff;
-                    const float2 u2 = make_float2(16777216.f, 16777216.f);
-                    const float2 ra = __fmul2_rn(sum[j][0], u2), rb = __fmul2_rn(sum[j][1], u2);
-                    const uint32_t q = quantise4(ra.x, ra.y, rb.x, rb.y);
-                    // predicated store, no branch: rows outside [ys, ye) (warm-up rows, rows of the next segment) are skipped
-                    const uint32_t ok = (all_rows || (ybase + yoff >= ys && ybase + yoff < ye)) ? 1u : 0u;
-                    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.u32 [%0], %1;\n\t}" ::"l"(orow), "r"(q), "r"(ok) : "memory");
+                for (int j = 0; j < RB; j++) {
+                    if ((S0 + j + A) % D != 0) continue;
+                    const int k = jj - (j - 4);
+                    if (k < 0 || k > 4) continue;
+                    const float2 kk = make_float2(kd[k], kd[k]);
+                    if (k == 0) { sum[j][0] = __fmul2_rn(xa, kk); sum[j][1] = __fmul2_rn(xb, kk); }
+                    else { sum[j][0] = __ffma2_rn(xa, kk, sum[j][0]); sum[j][1] = __ffma2_rn(xb, kk, sum[j][1]); }
+                    if (k == 4) {
+                        const int yoff = N * ((S0 + j + A - 2) / D);
+                        orow += (long long)(yoff - yprev) * opitch;
+                        yprev = yoff;
+                        const float2 u2 = make_float2(16777216.f, 16777216.f);
+                        const float2 ra = __fmul2_rn(sum[j][0], u2), rb = __fmul2_rn(sum[j][1], u2);
+                        const uint32_t q = quantise4(ra.x, ra.y, rb.x, rb.y);
+                        // rows outside [ys, ye) (warm-up rows, rows of the next segment) are skipped
+                        if (ALL || (ybase + yoff >= ys && ybase + yoff < ye)) *reinterpret_cast<uint32_t *>(orow) = q;
+                    }
                 }
             }
         }
-    }
+    };
+    if ((ybase >= ys) && (ybase + N * ((S0 + RB - 1 + A - 2) / D) < ye)) pass(std::true_type{}); else pass(std::false_type{});
 }
 
 // col: shared address of the lane's column in ring row 0; slot_it: ring slot of the iteration's first row; yit / op:
