@@ -108,6 +108,14 @@ __device__ __forceinline__ float fma_keep_denormals(float a, float b, float c) {
     return d;
 }
 
+__device__ __forceinline__ float2 ffma2_keep_denormals(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+
 template <class G>
 struct __align__(128) SmemD {             // one per warp
     uint8_t in[G::STAGES][G::STAGE_B];    // TMA destinations, row lr at lr * BOX_B
@@ -322,13 +330,18 @@ lanczos_dyn_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
                     xa[0] = a0 * kDenUnscale;
                     xa[3] = a3 * kDenUnscale;
                 }
+                // the other samples two at a time: one FFMA2 per tap for both (each with its own weights; same rounding
+                // as two FFMAs, one issue slot)
 #pragma unroll
-                for (int e = SHARE ? 1 : 0; e < (SHARE ? 3 : 4); e++) {
-                    float acc = -guard * kDenGuard;
+                for (int e = SHARE ? 1 : 0; e < (SHARE ? 3 : 4); e += 2) {
+                    float2 acc = make_float2(-guard * kDenGuard, -guard * kDenGuard);
 #pragma unroll
                     for (int k = 0; k < TAPS; k++)
-                        acc = fma_keep_denormals(__uint_as_float((uint32_t)row[off[e] + k * C]), wq[e][k], acc);
-                    xa[e] = acc * kDenUnscale;
+                        acc = ffma2_keep_denormals(make_float2(__uint_as_float((uint32_t)row[off[e] + k * C]), __uint_as_float((uint32_t)row[off[e + 1] + k * C])),
+                                                   make_float2(wq[e][k], wq[e + 1][k]), acc);
+                    const float2 r = __fmul2_rn(acc, make_float2(kDenUnscale, kDenUnscale));
+                    xa[e] = r.x;
+                    xa[e + 1] = r.y;
                 }
                 const uint32_t qa = quantise4(xa[0], xa[1], xa[2], xa[3]);
                 const uint32_t qb = quantise4(xa[0] + g2, xa[1] + g2, xa[2] + g2, xa[3] + g2);
