@@ -84,50 +84,6 @@ __device__ __forceinline__ uint8_t exact_taps(const uint8_t *tap0, int stride, W
     }
     return quantise_f64(sum);
 }
-// Sharper integer form of the phase-0 "cannot flip" filter (plan.cpp), used on the samples the
-// cheap fp32 filter flagged.  true = the reference provably returns v:
-//   half the spacing of doubles below v is h(v) = 2^ceil(log2 v) * 2^-54 (v a power of two: the
-//   spacing halves below it).  The running double sum stays >= v if the negative residues before
-//   the centre tap sum to <= h(v) and those after it are each <= h(v) (their sum is used, which is
-//   stricter).  ki[k] = ceil(|w_k| * 2^54 / 0.99 * 2^16), so "sum ki*b <= H << 16" is that test.
-template <int TAPS, int KM>
-__device__ __forceinline__ bool phase0_safe(const uint8_t *tap0, int stride, const int *ki) {
-    constexpr int CEN = TAPS / 2 - 1;
-    const int v = tap0[CEN * stride];
-    if (v == 0) return true;                               // the quantiser clamps at 0 either way
-    const int H = (v <= 1) ? 1 : (1 << (32 - __clz(v - 1)));
-    int pre = 0, post = 0;
-#pragma unroll
-    for (int k = 0; k < TAPS; k++)
-        if ((KM >> k) & 1) {
-            if (k < CEN) pre += ki[k] * (int)tap0[k * stride];
-            else post += ki[k] * (int)tap0[k * stride];
-        }
-    return pre <= (H << 16) && post <= (H << 16);
-}
-
-// Spread the set bits of every lane's `bits` over the warp: entries (lane << 5 | bit) [| 0x8000 if the bit is
-// also set in `gbits`] are written to the per-warp queue `q`; returns their number. `amask` must be a prefix
-// of the warp (lanes 0..n-1), every lane of it must call.
-__device__ __forceinline__ int warp_enqueue(uint32_t bits, uint32_t gbits, unsigned amask, int lane, uint16_t *q) {
-    const int cnt = __popc(bits);
-    int incl = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(amask, incl, d);
-        if (lane >= d) incl += t;
-    }
-    int pos = incl - cnt;
-    const int total = __shfl_sync(amask, incl, __popc(amask) - 1);
-    while (bits) {
-        const int b = __ffs(bits) - 1;
-        bits &= bits - 1;
-        q[pos++] = (uint16_t)((lane << 5) | b | (((gbits >> b) & 1u) << 15));
-    }
-    __syncwarp(amask);
-    return total;
-}
-
 using EncodeFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                               const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
