@@ -1068,6 +1068,12 @@ int launch_v6_one(const KParams &k, const FastHostTables &t, int *alias_in_kerne
         }
         if (cost < best_cost - 1e-9) { best_cost = cost; segs = sg_eff; }
     }
+    // LANCZOS_FLAG_INDEPENDENT: successive small launches of a stream overlap like the frames of a batch, so what counts
+    // is throughput, not the latency of one launch: about four launches' worth of warps resident at a time (measured on
+    // 1080p single frames, profiles/r02b_segs_independent.txt: 13 segments 11.6 us per frame, 27 segments -- what the
+    // latency model picks -- 13.3 us, 3 segments 16.2 us)
+    if ((k.flags & LANCZOS_FLAG_INDEPENDENT) && cols * 4 <= slots)
+        segs = std::max(1, std::min(max_segs, (int)std::lround((double)slots / (4.0 * (double)cols))));
     if (force_segs > 0) segs = std::min(force_segs, max_segs);
     int seg_periods = (vperiods + segs - 1) / segs;
     segs = (vperiods + seg_periods - 1) / seg_periods;
