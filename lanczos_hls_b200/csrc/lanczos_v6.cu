@@ -55,6 +55,9 @@
 #ifndef LZB_VCOLD_W
 #define LZB_VCOLD_W 4    // byte-columns per pass of the V pass's phase-0 second look (4 or 8)
 #endif
+#ifndef LZB_NOISY_AFTER
+#define LZB_NOISY_AFTER 2   // flagged chunks in a row after which a warp stops filtering phase-0 rows (huge = never)
+#endif
 #ifndef LZB_W
 #define LZB_W 1          // independent warps (strips) per CTA
 #endif
@@ -821,7 +824,7 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
     constexpr int NI_IT = viter_interp_rows<A, N, D, VU, G::S0>();
     const uint32_t zmask = p.strict_v_identity ? 0x80008000u : 0u;   // LANCZOS_FLAG_FAST_ALIGNED: phase-0 rows stay plain copies
 
-    auto v_pass = [&](int chunk) {
+    auto v_pass = [&](int chunk, bool noisy) -> bool {
         const int bslot = (chunk % G::REGIONS) * G::RB;
         const uint8_t *vrow = vcol + bslot * SWM;
         // rows [ybase, ybase + YROWS + N * (A + 2) / D] can be stored by this chunk
@@ -910,7 +913,9 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
                     //   until row r + 2 arrives).  The exact value (a multiple of 2^-27) is rounded once, to a multiple
                     //   of 2^-24, and rounding never changes the sign; 0.375 >= plan.cpp's K_k: a set sign bit means
                     //   "the reference may return v - 1" (v_fix_iter looks again).
-                    if ((s0 + A) % D == 0) {
+                    // (noisy, warp-uniform: the phase-0 rows of this chunk are all redone by v_fix_phase0_chunk anyway, see the
+                    // pipeline loop: no filter, no copies here)
+                    if ((s0 + A) % D == 0 && !noisy) {
                         const int zs = (ZD == 2) ? (u & 1) : 0;       // D = 1: slot of row r-2 = slot this row overwrites
                         uint2 qv;
                         if (FILTER) {
@@ -975,17 +980,25 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
                 op += (long long)(N * VU / D) * opitch;
             }
         };
-        if (interior) body(std::false_type{}); else body(std::true_type{});
-        // rare: the reference may return v - 1 somewhere in the phase-0 rows of this chunk -> all of them again, exactly
+        bool flagged = false;
         if constexpr (FILTER) {
-            if ((zchunk & zmask) != 0u)
+            if (interior) body(std::false_type{}); else body(std::true_type{});
+            flagged = noisy || (zchunk & zmask) != 0u;
+            // the reference may return v - 1 somewhere in the phase-0 rows of this chunk -> all of them again, exactly
+            // (rare on image-like content; in noisy mode this IS how the phase-0 rows are produced)
+            if (flagged)
                 v_fix_phase0_chunk<A, N, D, G::S0, G::RB, G::RING, SWM>(p, vcol_s, bslot, ybase, ocol, opitch, valid_bytes - VB * tid, ys, ye);
+        } else {
+            if (interior) body(std::false_type{}); else body(std::true_type{});
         }
         ybase += G::YROWS;
         ocol += (long long)G::YROWS * opitch;
+        return flagged;
     };
 
     // ------------------------------ pipeline ------------------------------
+    bool noisy = false;
+    int flagged_run = 0;
     for (int chunk = 0; chunk < nchunks; chunk++) {
 #ifndef LZB_ABL_NOH
         h_pass(chunk);
@@ -996,7 +1009,19 @@ lanczos_v6_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
         // every lane has read the TMA stage of this chunk: refill it with chunk + STAGES
         if (tid == 0 && chunk + G::STAGES < nchunks) issue(chunk + G::STAGES);
 #ifndef LZB_ABL_NOV
-        if (v_active) v_pass(chunk);
+        bool flagged = false;
+        if (v_active) flagged = v_pass(chunk, noisy);
+        // Content that keeps flagging the phase-0 filter (noise, dark noise): after two flagged chunks in a row the warp
+        // stops filtering for the rest of its segment -- the chunk-wise exact pass produces the phase-0 rows, the hot loop
+        // only the interpolated ones (warp-uniform; a warp works on one strip x segment of one frame).  One loop body
+        // with a uniform branch around the filter: separate loop bodies for the two modes grew the chunk loop from 16 to
+        // 23 KB of code and cost image-like content 2.6 % (measured), the branch costs it 0.5 %.
+        if constexpr (FILTER) {
+            if (!noisy) {
+                flagged_run = __any_sync(0xffffffffu, flagged) ? flagged_run + 1 : 0;
+                noisy = flagged_run >= LZB_NOISY_AFTER;
+            }
+        }
 #endif
         // in-place top rows of the reference: replayed exactly once rows 0..alias_top_row+A are in the ring
         if (p.alias_rows > 0 && ys == 0 && v_active && chunk == (nchunks > 1 ? 1 : 0)) {
