@@ -456,6 +456,49 @@ def test_specialised_kernels_bit_exact(torch_cuda, lz, oracle, cfg, kind):
     assert st["n_diff"] == 0, st
 
 
+def patchwork_hwc(oracle, h, w, c, seed, band, col):
+    """Image-like, uniform-noise and dark-noise patches side by side: `band` rows x `col` pixels each, in turn."""
+    kinds = [smooth_hwc(oracle, h, w, c, seed), noise_hwc(oracle, h, w, c, seed + 1), dark_hwc(oracle, h, w, c, seed + 2)]
+    yy, xx = np.mgrid[0:h, 0:w]
+    sel = ((yy // band) + (xx // col)) % 3
+    img = np.zeros((h, w, c), dtype=np.uint8)
+    for k in range(3):
+        img[sel == k] = kinds[k][sel == k]
+    return img
+
+
+@pytest.mark.parametrize("cfg", [  # in_w, in_h, n, d, a, c, kernel id, patch rows, patch pixels
+    (704, 420, 2, 1, 3, 3, 1, 37, 150), (704, 420, 2, 1, 3, 3, 1, 9, 40), (704, 300, 2, 1, 3, 3, 1, 150, 704),
+    (512, 300, 3, 2, 3, 4, 3, 31, 100), (512, 300, 2, 1, 3, 4, 2, 23, 512),
+], ids=lambda c: "x".join(map(str, c)))
+def test_patchwork_content_switches_phase0_modes(torch_cuda, lz, oracle, cfg):
+    """The phase-0 second look has three regimes inside one vertical segment of one strip -- filter clean, chunk flagged
+    (exact chunk pass after the hot loop), warp in noisy mode (no filter, every phase-0 row from the exact chunk pass) --
+    and switches between them at chunk boundaries: patches of image-like content, uniform noise and dark noise of
+    several sizes (smaller than a chunk, a few chunks, wider than a strip) exercise every transition, whole image and as
+    row bands."""
+    iw, ih, n, d, a, c, kid, band, col = cfg
+    ow, oh = oracle.out_dims(iw, ih, n, d)
+    img = patchwork_hwc(oracle, ih, iw, c, seed=iw + band, band=band, col=col)
+    want = oracle.upscale(img, ow, oh, a, n, d, variant=oracle.VERBATIM)
+    got = gpu_upscale(torch_cuda, lz, img, ow, oh, a, n, d)
+    assert lz.stats()["kernel_id"] == kid
+    st = diff_stats(got, want)
+    assert st["n_diff"] == 0, st
+    # the same as three row bands (other segment boundaries, the flag state starts afresh in every band)
+    desc = lz.make_desc(iw, ih, ow, oh, c, a, n, d)
+    out = np.zeros_like(want)
+    edges = [0, oh // 3 + 1, 2 * oh // 3 - 1, oh]
+    for r0, r1 in zip(edges[:-1], edges[1:]):
+        in0, inn = lz.band_input_rows(desc, r0, r1 - r0)
+        d_in = torch_cuda.from_numpy(np.ascontiguousarray(img[in0:in0 + inn])).cuda()
+        d_out = torch_cuda.zeros((r1 - r0, ow, c), dtype=torch_cuda.uint8, device="cuda")
+        lz.upscale_band_device(desc, d_in, d_out, r0, r1 - r0, in0, inn)
+        torch_cuda.cuda.synchronize()
+        out[r0:r1] = d_out.cpu().numpy()
+    assert np.array_equal(out, want)
+
+
 @pytest.mark.parametrize("cfg", [(960, 540, 2, 1, 3, 3), (640, 360, 3, 2, 3, 4), (240, 97, 2, 1, 3, 3)],
                          ids=lambda c: "x".join(map(str, c)))
 def test_tolerance_mode_is_within_one_lsb(torch_cuda, lz, oracle, cfg):
