@@ -1,5 +1,5 @@
 """Randomised differential test: CUDA path (C ABI) vs the CPU oracle on many small random shapes, ratios,
-contents and layouts.  usage: [FUZZ_MAXW=300 FUZZ_MAXH=120] python tools/fuzz_parity.py [seconds] [seed]
+contents (noise, image-like, dark noise, patchworks of the three) and layouts.  usage: [FUZZ_MAXW=300 FUZZ_MAXH=120] python tools/fuzz_parity.py [seconds] [seed]
 (needs a GPU; exits 1 on a mismatch)"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -24,8 +24,17 @@ while time.time() - t0 < budget:
     ow, oh = O.out_dims(iw, ih, nn, dd)
     if ow < 1 or oh < ih:
         continue
-    kind = rng.integers(3)
-    img = [noise_hwc, smooth_hwc, dark_hwc][kind](O, ih, iw, c, seed=int(rng.integers(1 << 20)))
+    kind = rng.integers(4)
+    if kind < 3:
+        img = [noise_hwc, smooth_hwc, dark_hwc][kind](O, ih, iw, c, seed=int(rng.integers(1 << 20)))
+    else:                                        # patchwork of the three (the phase-0 regimes switch inside a segment)
+        sd, band, col = int(rng.integers(1 << 20)), int(rng.integers(3, 60)), int(rng.integers(8, 400))
+        parts = [f(O, ih, iw, c, seed=sd + i) for i, f in enumerate((smooth_hwc, noise_hwc, dark_hwc))]
+        yy, xx = np.mgrid[0:ih, 0:iw]
+        sel = ((yy // band) + (xx // col)) % 3
+        img = np.zeros((ih, iw, c), dtype=np.uint8)
+        for i in range(3):
+            img[sel == i] = parts[i][sel == i]
     flags = int(rng.choice([0, 0, lz.FLAG_NO_ALIAS]))
     variant = O.CLEAN if flags & lz.FLAG_NO_ALIAS else O.VERBATIM
     mode = rng.integers(3)
