@@ -74,7 +74,9 @@ enum {
      * bench.py and asserted in tests/ (> 0.999 on image-like content). */
     LANCZOS_FLAG_TOLERANCE_1LSB = 1u << 3,
     /* Device-buffer entry points only: the caller promises that this call reads nothing that earlier work on the same
-     * CUDA stream is still writing (independent frames of a video, one call per frame).  The kernel is then launched
+     * CUDA stream is still writing, and writes nothing that earlier work is still reading or writing -- independent
+     * frames of a video, one call per frame, each with its OWN output buffer (two consecutive calls into the same
+     * output buffer may overlap in time).  The kernel is then launched
      * with programmatic dependent launch and does not wait for the previous kernel of the stream, so consecutive
      * single-frame calls overlap on the GPU like the frames of one batch launch instead of running back to back
      * (BASELINE configs[1] read literally: one 1080p frame per call).  Later work on the stream still waits for the
