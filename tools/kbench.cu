@@ -1,6 +1,6 @@
 // kbench.cu -- C++ development harness around the C ABI (no Python, starts in a second on a fresh box).
 //   tools/bin/kbench IN_W IN_H N D A C FRAMES CONTENT ITERS [FLAGS] [CMP_IMPL]
-// CONTENT: smooth | noise | dark.   Runs lanczos_b200_upscale_batch ITERS times (CUDA events), prints
+// CONTENT: smooth | noise | dark | mix (even frames smooth, odd frames noise).   Runs lanczos_b200_upscale_batch ITERS times (CUDA events), prints
 // Gpix/s, GB/s of algorithmic traffic and an FNV-1a hash of the output.  If CMP_IMPL is given (any word, e.g.
 // "generic") the same call is repeated with LANCZOS_FLAG_GENERIC_KERNEL (an independent implementation inside
 // the library: per-coordinate weights, one thread per output pixel) and the two outputs are compared byte for
@@ -33,7 +33,7 @@ __global__ void fill_kernel(uint8_t *img, long long n, int w, int h, int c, int 
         const int x = (int)(px % w), y = (int)((px / w) % h), f = (int)(px / ((long long)w * h));
         const uint32_t r = mix((uint32_t)i * 2654435761u + (uint32_t)(i >> 32) + 12345u);
         int v;
-        if (content == 1) v = r & 255;
+        if (content == 1 || (content == 3 && (f & 1))) v = r & 255;      // content 3: even frames smooth, odd frames noise
         else if (content == 2) v = r & 15;
         else {
             const float b = 128.f + 90.f * sinf(0.05f * x + ch + 0.3f * f) * cosf(0.037f * y);
@@ -69,7 +69,7 @@ int main(int argc, char **argv) {
     const unsigned flags = argc > 10 ? (unsigned)strtoul(argv[10], nullptr, 0) : 0u;
     const char *cmp_impl = argc > 11 ? argv[11] : nullptr;
     const int ow = (int)((long long)iw * n / d), oh = (int)((long long)ih * n / d);
-    const int ct = content == "noise" ? 1 : (content == "dark" ? 2 : 0);
+    const int ct = content == "noise" ? 1 : (content == "dark" ? 2 : (content == "mix" ? 3 : 0));
 
     lanczos_desc desc{};
     desc.in_w = iw; desc.in_h = ih; desc.out_w = ow; desc.out_h = oh; desc.channels = c; desc.a = a;
