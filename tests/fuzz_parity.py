@@ -1,5 +1,5 @@
 """Randomised differential test: CUDA path (C ABI) vs the CPU oracle on many small random shapes, ratios,
-contents (noise, image-like, dark noise, patchworks of the three) and layouts.  usage: [FUZZ_MAXW=300 FUZZ_MAXH=120] python tools/fuzz_parity.py [seconds] [seed]
+contents (noise, image-like, dark noise, patchworks of the three) and layouts.  usage: [FUZZ_MAXW=300 FUZZ_MAXH=120] python tests/fuzz_parity.py [seconds] [seed]
 (needs a GPU; exits 1 on a mismatch)"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -4,12 +4,12 @@ reference, tests/test_oracle.py) upscales one 16384x16384 RGB8 uniform-noise ima
 the FNV-1a-64 of the interleaved output goes to tests/golden/c5_hash.txt.  About 15 minutes on 8 cores; run once in the
 build container.  tests/test_gpu_parity.py::test_config5_full_size_hash recomputes the input on the GPU box (same
 xorshift seed), runs the row-band API and compares hashes: no 2.3 GB fixture travels.
-  python tools/make_c5_hash.py [size]"""
+  python tests/golden/make_c5_hash.py [size]"""
 import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import oracle_py as O  # noqa: E402
 
@@ -25,6 +25,6 @@ lines = []
 if os.path.exists(path):
     lines = [ln for ln in open(path) if not ln.startswith(f"{size} ")]
 if not lines:
-    lines = ["# in_w in_h out_w out_h n d a c fnv1a64(oracle output, interleaved y,x,c) ; input = xorshift seed SEED+5 interleaved; tools/make_c5_hash.py\n"]
+    lines = ["# in_w in_h out_w out_h n d a c fnv1a64(oracle output, interleaved y,x,c) ; input = xorshift seed SEED+5 interleaved; tests/golden/make_c5_hash.py\n"]
 open(path, "w").writelines(lines + [line])
 print(line.strip(), f"({time.time() - t0:.0f} s)")

@@ -375,7 +375,7 @@ def c5_hashes():
 @pytest.mark.parametrize("cfg", c5_hashes(), ids=lambda c: "%dsq" % c[0])
 def test_config5_full_size_hash(torch_cuda, lz, oracle, cfg):
     """BASELINE configs[4] at its LITERAL size (16384^2 -> 27852^2, 17/10) against the oracle: the oracle's output
-    was hashed once in the build container (tools/make_c5_hash.py -> tests/golden/c5_hash.txt); here the same
+    was hashed once in the build container (tests/golden/make_c5_hash.py -> tests/golden/c5_hash.txt); here the same
     xorshift input is regenerated, upscaled as 8 row bands (each with its own halo rows) and the FNV-1a-64 of the
     interleaved result compared."""
     torch = torch_cuda
